@@ -1,0 +1,86 @@
+// bsb_common.cuh -- shared declarations for libblackstar_b200 (sm_100a only).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define BSB_HD __host__ __device__ __forceinline__
+#define BSB_D __device__ __forceinline__
+#else
+#define BSB_HD inline
+#define BSB_D inline
+#endif
+
+namespace bsb {
+
+// Star record in device memory: bsb_star (include/blackstar_b200.h) permuted into
+// k-d leaf order.  48 bytes, 16-byte aligned.
+struct StarRec {
+    double x, y, z;
+    double hue, sat;
+    int32_t mag;
+    int32_t pad;
+};
+static_assert(sizeof(StarRec) == 48, "StarRec must mirror bsb_star");
+
+// Bucketed k-d tree over the unit-sphere star positions (DESIGN.md "star map").
+//   internal nodes: implicit complete binary tree in heap order, n_internal = 2^depth - 1;
+//   split[i] holds the split coordinate with the split axis (0,1,2) in the two lowest
+//   mantissa bits; points with coord <= split go left, >= split go right.
+//   leaf l (0 <= l < 2^depth) owns stars [leaf_off[l], leaf_off[l+1]).
+struct StarTreeDev {
+    const double *split;
+    const uint32_t *leaf_off;
+    const StarRec *stars;
+    int32_t depth;
+    int32_t n_stars;
+};
+
+constexpr int kSmemTreeLevels = 12;                       // top levels staged in shared memory
+constexpr int kSmemTreeNodes = (1 << kSmemTreeLevels) - 1; // 4095 doubles = 32 KB
+
+// Everything a ray needs that is constant over the frame.  Passed by value as a
+// __grid_constant__ kernel parameter (constant bank, warp-uniform loads).
+struct FrameParams {
+    // camera: src/Raytracer.hs:40-51
+    double cam[3];            // position
+    double xa[3], ya[3], za[3]; // rows of lookAt's 3x3 are xa, ya, -za
+    double fov;
+    double e1[3];             // cam / |cam| : first axis of every ray's orbital plane
+    double r0;                // |cam|
+    double q0;                // quadrance cam (as the reference sums it)
+    // integrator: src/Raytracer.hs:113-134
+    double h;                 // stepSize
+    double hh;                // h/2
+    double h6;                // h/6
+    double hh2;               // (h/2)^2
+    double hhh;               // h*(h/2)
+    double hsq6;              // h*h/6
+    // termination / disk: src/Raytracer.hs:58-65, 88-111
+    double safe2, din2, dout2;
+    double r_in, r_out;       // sqrt of din2, dout2 (diskColor' recomputes them per hit)
+    double disk_rgb[3];
+    double disk_opacity;
+    // sky: src/StarMap.hs:93-115
+    double star_intensity, star_saturation;
+    StarTreeDev tree;
+    // grid
+    int32_t W2, H2;           // traced grid (doubled under supersampling)
+    int32_t W, H;             // final image
+    int32_t ss;               // supersampling 0/1
+    int32_t row0, row1;       // final-image rows rendered by this launch
+    int32_t tiles_x, tiles_y, n_tiles;
+    uint32_t step_cap;        // the reference has no cap (Raytracer.hs:80-85); ours is a safety net
+};
+
+// Per-launch counters (device memory, zeroed before the launch).
+struct TraceCounters {
+    unsigned long long steps;
+    unsigned long long capped;
+    unsigned long long star_hits;
+    unsigned int next_tile;
+    unsigned int pad;
+};
+
+}  // namespace bsb

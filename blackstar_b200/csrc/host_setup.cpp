@@ -1,0 +1,224 @@
+// host_setup.cpp -- see host_setup.hpp.  Compiled with -ffp-contract=off: the per-frame
+// constants are formed with the reference's operation order so the device starts from
+// bit-identical inputs.
+#include "host_setup.hpp"
+
+#include "trace_core.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace bsb {
+
+namespace {
+
+struct V3 { double x, y, z; };
+
+inline V3 sub(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline double quadrance(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+// Linear.V3.cross
+inline V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+// Linear.Metric.normalize (nearZero = |a| <= 1e-12)
+inline V3 normalize(V3 v)
+{
+    const double l = quadrance(v);
+    if (std::fabs(l) <= 1e-12 || std::fabs(1 - l) <= 1e-12) return v;
+    const double s = std::sqrt(l);
+    return { v.x / s, v.y / s, v.z / s };
+}
+
+}  // namespace
+
+void host_hsi_to_rgb(double h, double s, double i, double rgb[3]) { hsi_to_rgb(h, s, i, rgb); }
+
+std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int row0, int row1, FrameParams &P)
+{
+    if (scn.width <= 0 || scn.height <= 0) return "resolution must be positive";
+    if (scn.width > 32768 || scn.height > 32768) return "resolution above 32768 is not supported";
+    if (row0 < 0 || row1 > scn.height || row0 > row1) return "row range outside the image";
+    if (!(scn.step_size > 0) || !std::isfinite(scn.step_size)) return "stepSize must be a positive finite number";
+    const double all[] = { cam.pos[0], cam.pos[1], cam.pos[2], cam.look_at[0], cam.look_at[1], cam.look_at[2],
+                           cam.up[0], cam.up[1], cam.up[2], cam.fov, scn.disk_opacity, scn.disk_inner,
+                           scn.disk_outer, scn.star_intensity, scn.star_saturation, scn.disk_hsi[0],
+                           scn.disk_hsi[1], scn.disk_hsi[2] };
+    for (double v : all)
+        if (!std::isfinite(v)) return "non-finite camera/scene value";
+
+    std::memset(&P, 0, sizeof P);
+    const V3 eye = { cam.pos[0], cam.pos[1], cam.pos[2] };
+    const V3 center = { cam.look_at[0], cam.look_at[1], cam.look_at[2] };
+    const V3 up = { cam.up[0], cam.up[1], cam.up[2] };
+    // Linear.Projection.lookAt (src/Raytracer.hs:47)
+    const V3 za = normalize(sub(center, eye));
+    const V3 xa = normalize(cross(za, up));
+    const V3 ya = cross(xa, za);
+    P.cam[0] = eye.x; P.cam[1] = eye.y; P.cam[2] = eye.z;
+    P.xa[0] = xa.x; P.xa[1] = xa.y; P.xa[2] = xa.z;
+    P.ya[0] = ya.x; P.ya[1] = ya.y; P.ya[2] = ya.z;
+    P.za[0] = za.x; P.za[1] = za.y; P.za[2] = za.z;
+    P.fov = cam.fov;
+    P.q0 = quadrance(eye);
+    P.r0 = std::sqrt(P.q0);
+    if (P.r0 > 0) {
+        P.e1[0] = eye.x / P.r0; P.e1[1] = eye.y / P.r0; P.e1[2] = eye.z / P.r0;
+    } else {
+        P.e1[0] = 1; P.e1[1] = 0; P.e1[2] = 0;  // camera at the singularity: every ray is black (r2 < 1)
+    }
+    const double h = scn.step_size;
+    P.h = h;
+    P.hh = h / 2;
+    P.h6 = h / 6;
+    P.hh2 = (h / 2) * (h / 2);
+    P.hhh = h * (h / 2);
+    P.hsq6 = h * h / 6;
+    // src/Raytracer.hs:59-62
+    const double twoq = 2 * P.q0;
+    P.safe2 = 2500.0 > twoq ? 2500.0 : twoq;
+    P.din2 = scn.disk_inner * scn.disk_inner;
+    P.dout2 = scn.disk_outer * scn.disk_outer;
+    P.r_in = std::sqrt(P.din2);   // diskColor' takes sqrt of the squared radii (:107-108)
+    P.r_out = std::sqrt(P.dout2);
+    hsi_to_rgb(scn.disk_hsi[0], scn.disk_hsi[1], scn.disk_hsi[2], P.disk_rgb);  // :65
+    if (scn.disk_opacity != 0 && !(std::isfinite(P.disk_rgb[0])))
+        return "diskColor hue outside [0, 360)";  // massiv-io raises `error` here
+    P.disk_opacity = scn.disk_opacity;
+    P.star_intensity = scn.star_intensity;
+    P.star_saturation = scn.star_saturation;
+    P.ss = scn.supersampling ? 1 : 0;
+    P.W = scn.width; P.H = scn.height;
+    P.W2 = P.ss ? 2 * scn.width : scn.width;   // :58
+    P.H2 = P.ss ? 2 * scn.height : scn.height;
+    P.row0 = row0; P.row1 = row1;
+    const int rows = row1 - row0;
+    if (P.ss) {  // a warp = 4x2 output pixels = 8x4 rays
+        P.tiles_x = (P.W + 3) / 4;
+        P.tiles_y = (rows + 1) / 2;
+    } else {     // a warp = 8x4 pixels
+        P.tiles_x = (P.W + 7) / 8;
+        P.tiles_y = (rows + 3) / 4;
+    }
+    P.n_tiles = P.tiles_x * P.tiles_y;
+    P.step_cap = 1000000u;
+    return "";
+}
+
+// ------------------------------------------------------------------ k-d tree
+namespace {
+
+struct Builder {
+    const bsb_star *s;
+    std::vector<uint32_t> idx;
+    HostStarTree *t;
+    int depth;
+
+    void rec(size_t node, int level, size_t lo, size_t hi)
+    {
+        if (level == depth) {
+            const size_t leaf = node - ((size_t(1) << depth) - 1);
+            t->leaf_off[leaf] = (uint32_t)lo;
+            t->leaf_off[leaf + 1] = (uint32_t)hi;  // leaves are visited left to right
+            return;
+        }
+        int axis = 0;
+        double sv = 0.0;
+        size_t mid = lo;
+        if (hi > lo) {
+            double mn[3] = { 2, 2, 2 }, mx[3] = { -2, -2, -2 };
+            for (size_t k = lo; k < hi; k++)
+                for (int a = 0; a < 3; a++) {
+                    const double c = s[idx[k]].pos[a];
+                    mn[a] = std::min(mn[a], c);
+                    mx[a] = std::max(mx[a], c);
+                }
+            const double ex[3] = { mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2] };
+            axis = (ex[1] > ex[0]) ? 1 : 0;
+            if (ex[2] > ex[axis]) axis = 2;
+            mid = lo + (hi - lo) / 2;
+            const bsb_star *sp = s;
+            const int ax = axis;
+            std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                             [sp, ax](uint32_t a, uint32_t b) { return sp[a].pos[ax] < sp[b].pos[ax]; });
+            sv = s[idx[mid]].pos[axis];
+        }
+        uint64_t bits;
+        std::memcpy(&bits, &sv, 8);
+        bits = (bits & ~uint64_t(3)) | uint64_t(axis);
+        std::memcpy(&t->split[node], &bits, 8);
+        rec(2 * node + 1, level + 1, lo, mid);
+        rec(2 * node + 2, level + 1, mid, hi);
+    }
+};
+
+}  // namespace
+
+void build_star_tree(const bsb_star *stars, size_t n, int leaf_size, HostStarTree &out)
+{
+    if (leaf_size < 1) leaf_size = 1;
+    int depth = 0;
+    while ((size_t(leaf_size) << depth) < n && depth < 24) depth++;
+    out.depth = depth;
+    out.split.assign((size_t(1) << depth) - 1 + 1, 0.0);  // +1: never zero-sized
+    out.leaf_off.assign((size_t(1) << depth) + 1, 0u);
+    Builder b{ stars, std::vector<uint32_t>(n), &out, depth };
+    std::iota(b.idx.begin(), b.idx.end(), 0u);
+    b.rec(0, 0, 0, n);
+    out.stars.resize(n);
+    for (size_t k = 0; k < n; k++) {
+        const bsb_star &s = stars[b.idx[k]];
+        out.stars[k] = StarRec{ s.pos[0], s.pos[1], s.pos[2], s.hue, s.sat, s.mag, 0 };
+    }
+}
+
+// ------------------------------------------------------------------ PPM catalogue
+namespace {
+
+double f64be(const uint8_t *p)
+{
+    uint64_t u = 0;
+    for (int k = 0; k < 8; k++) u = (u << 8) | p[k];
+    double d;
+    std::memcpy(&d, &u, 8);
+    return d;
+}
+
+// starColor (src/StarMap.hs:63-72)
+void spectral_colour(int ch, double &hue, double &sat)
+{
+    switch (ch) {
+    case 'O': hue = 0.631; sat = 0.39; break;
+    case 'B': hue = 0.628; sat = 0.33; break;
+    case 'A': hue = 0.622; sat = 0.21; break;
+    case 'F': hue = 0.650; sat = 0.03; break;
+    case 'G': hue = 0.089; sat = 0.09; break;
+    case 'K': hue = 0.094; sat = 0.29; break;
+    case 'M': hue = 0.094; sat = 0.56; break;
+    default: hue = 0; sat = 0; break;
+    }
+}
+
+}  // namespace
+
+bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err)
+{
+    if (len < 28) { err = "too few bytes"; return false; }  // cereal's message for a failed `skip 28`
+    const size_t n = (len - 28) / 28;                       // :48-49 remaining `div` 28
+    out.resize(n);
+    const uint8_t *p = bytes + 28;
+    for (size_t k = 0; k < n; k++, p += 28) {
+        const double ra = f64be(p), dec = f64be(p + 8);      // :50-51
+        const int spectral = p[16];                          // :52, then skip 1
+        const int16_t mag = (int16_t)(uint16_t(p[18]) << 8 | p[19]);  // :54, then skip 8
+        bsb_star &s = out[k];
+        s.pos[0] = std::cos(dec) * std::cos(ra);             // :74-75 raDecToCartesian
+        s.pos[1] = std::cos(dec) * std::sin(ra);
+        s.pos[2] = std::sin(dec);
+        s.mag = mag;
+        s.pad_ = 0;
+        spectral_colour(spectral, s.hue, s.sat);
+    }
+    return true;
+}
+
+}  // namespace bsb

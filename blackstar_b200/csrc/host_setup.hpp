@@ -1,0 +1,36 @@
+// host_setup.hpp -- host-side preparation for the kernels: frame constants (the part of
+// Raytracer.render that runs once per frame, src/Raytracer.hs:53-65), the bucketed k-d tree
+// over the star list (replaces kdt's `build`, src/StarMap.hs:91), and the PPM catalogue
+// reader (StarMap.readMap, src/StarMap.hs:45-58).
+#pragma once
+
+#include "../../include/blackstar_b200.h"
+#include "bsb_common.cuh"
+
+#include <string>
+#include <vector>
+
+namespace bsb {
+
+// Fills every field of FrameParams except `tree` (device pointers).  Returns "" or an
+// error message (invalid scene).
+std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int row0, int row1,
+                              FrameParams &P);
+
+struct HostStarTree {
+    std::vector<double> split;       // 2^depth - 1 entries, axis in the 2 low mantissa bits
+    std::vector<uint32_t> leaf_off;  // 2^depth + 1 entries
+    std::vector<StarRec> stars;      // leaf order
+    int depth = 0;
+};
+
+// Median-split k-d tree with buckets of <= ~leaf_size stars; widest-extent split axis.
+void build_star_tree(const bsb_star *stars, size_t n, int leaf_size, HostStarTree &out);
+
+// StarMap.readMap + starColor' : PPM binary catalogue -> flat star list.
+bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err);
+
+// massiv-io HSI -> RGB on the host (disk colour, once per frame; src/Raytracer.hs:65)
+void host_hsi_to_rgb(double h, double s, double i, double rgb[3]);
+
+}  // namespace bsb

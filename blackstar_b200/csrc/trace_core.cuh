@@ -1,0 +1,353 @@
+// trace_core.cuh -- per-ray arithmetic of the geodesic tracer (K1) and the sky lookup (K2).
+//
+// Written as __host__ __device__ so the SAME source is (a) inlined into the sm_100a kernels
+// of trace_kernel.cu and (b) compiled for the host by tests/hostcheck (a test-only harness
+// that diffs this arithmetic against the oracle without a GPU).  The shipped library never
+// runs the host instantiation: there is no CPU fallback.
+//
+// Reference semantics: src/Raytracer.hs:34-134, src/StarMap.hs:93-115.
+//
+// B200-first restructuring:
+//  * every ray's motion is planar (the force is central), and classical RK4 commutes with
+//    rotations, so the reference's 6-double state (vel, pos) is integrated as 4 doubles
+//    (u, v, du, dv) in the orthonormal basis (e1, e2) of the ray's own orbital plane, with
+//    e1 = cam/|cam| shared by the whole frame.  In exact arithmetic this is the SAME discrete
+//    map as the reference's 3-D RK4 (same truncation error); only rounding (1e-16) differs.
+//  * |pos|^-5 comes from one MUFU.RSQ64H seed + a third-order correction (9 DP ops) instead
+//    of sqrt, three multiplies and a divide;
+//  * the stage velocities are eliminated algebraically (p3 = p2 + (h/2)^2 a1, ...), 72 DP
+//    instructions per step instead of the ~141 flops of the reference as written.
+#pragma once
+
+#include "bsb_common.cuh"
+
+#include <cmath>
+
+namespace bsb {
+
+// ---- correctly-rounded primitives that must never be contracted into FMAs ------------
+#if defined(__CUDA_ARCH__)
+BSB_D double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+BSB_D double add_rn(double a, double b) { return __dadd_rn(a, b); }
+BSB_D double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+BSB_D double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+BSB_D double sqrt_rn(double a) { return __dsqrt_rn(a); }
+BSB_D double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+#else
+// host instantiation (tests/hostcheck only), compiled with -ffp-contract=off
+inline double mul_rn(double a, double b) { return a * b; }
+inline double add_rn(double a, double b) { return a + b; }
+inline double sub_rn(double a, double b) { return a - b; }
+inline double div_rn(double a, double b) { return a / b; }
+inline double sqrt_rn(double a) { return std::sqrt(a); }
+inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
+#endif
+
+// Seed for x^-1/2.  Device: MUFU.RSQ64H via rsqrt.approx.ftz.f64 (looks at the high word of
+// x only; ~20 good bits).  Host: an emulation with the same information loss, so hostcheck
+// exercises the correction polynomial at the accuracy the hardware seed has.
+BSB_HD double rsqrt_seed(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    union { double d; uint64_t u; } a, b;
+    a.d = x;
+    a.u &= 0xFFFFFFFF00000000ull;             // hardware reads the high 32 bits only
+    b.d = (double)(float)(1.0 / std::sqrt(a.d)); // ~24-bit result
+    b.u &= 0xFFFFFFFF00000000ull;
+    return b.d;
+#endif
+}
+
+// k * q^(-5/2), relative error ~2 ulp.  With y0 = q^-1/2 (1+d) and e = 1 - q y0^2 = -(2d + d^2):
+//   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + O(e^3)),  |e| <~ 2^-19.
+BSB_HD double rinv5k(double q, double k)
+{
+    const double y0 = rsqrt_seed(q);
+    const double t = q * y0;
+    const double e = fma_(-t, y0, 1.0);
+    const double p = fma_(4.375, e, 2.5);
+    const double y2 = y0 * y0;
+    const double y4 = y2 * y2;
+    const double yk = y0 * k;
+    const double y5k = y4 * yk;
+    const double ep = e * p;
+    return fma_(y5k, ep, y5k);
+}
+
+// ---- ray generation: src/Raytracer.hs:40-51, bit-exact with the reference's op order ----
+BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
+{
+    const double w = (double)P.W2, h = (double)P.H2;
+    const double vx = mul_rn(P.fov, sub_rn(div_rn((double)x, w), 0.5));                 // :49
+    const double vy = div_rn(mul_rn(mul_rn(P.fov, sub_rn(0.5, div_rn((double)y, h))), h), w); // :50
+    double u[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)  // :48  (xa_i*vx + ya_i*vy) + (-za_i)*(-1)
+        u[k] = add_rn(add_rn(mul_rn(P.xa[k], vx), mul_rn(P.ya[k], vy)), P.za[k]);
+    // Linear.normalize: unchanged if |v|^2 is within 1e-12 of 0 or 1
+    const double l = add_rn(add_rn(mul_rn(u[0], u[0]), mul_rn(u[1], u[1])), mul_rn(u[2], u[2]));
+    if (fabs(l) <= 1e-12 || fabs(sub_rn(1.0, l)) <= 1e-12) {
+        dir[0] = u[0]; dir[1] = u[1]; dir[2] = u[2];
+    } else {
+        const double s = sqrt_rn(l);
+        dir[0] = div_rn(u[0], s); dir[1] = div_rn(u[1], s); dir[2] = div_rn(u[2], s);
+    }
+}
+
+// State of one ray between step blocks.
+struct RayState {
+    double u, v;       // position in the (e1, e2) plane
+    double du, dv;     // velocity in the plane
+    double q;          // |pos|^2 of the current position
+    double y;          // scene-y of the current position (disk plane is y = 0)
+    double k;          // -1.5 * h2
+    double e2y;        // y component of e2
+    double acc[4];     // colour accumulated front-to-back (premultiplied RGBA), Raytracer.hs:86
+    uint32_t steps;
+    int32_t status;    // kAlive / kBlack / kSky / kCapped
+};
+enum : int32_t { kAlive = 0, kBlack = 1, kSky = 2, kCapped = 3, kIdle = 4 };
+
+// orbital-plane basis for direction `dir`: a = dir.e1, b = |dir - a e1|, e2 = (dir - a e1)/b
+BSB_HD void plane_basis(const FrameParams &P, const double dir[3], double &a, double &b, double e2[3])
+{
+    a = dir[0] * P.e1[0] + dir[1] * P.e1[1] + dir[2] * P.e1[2];
+    double w0 = fma_(-a, P.e1[0], dir[0]);
+    double w1 = fma_(-a, P.e1[1], dir[1]);
+    double w2 = fma_(-a, P.e1[2], dir[2]);
+    const double b2 = w0 * w0 + w1 * w1 + w2 * w2;
+    if (b2 < 1e-60) {
+        // radial ray: any unit vector orthogonal to e1 will do (h2 = 0, the motion is a line)
+        const double ax = fabs(P.e1[0]), ay = fabs(P.e1[1]), az = fabs(P.e1[2]);
+        double t0 = 0, t1 = 0, t2 = 0;
+        if (ax <= ay && ax <= az) t0 = 1; else if (ay <= az) t1 = 1; else t2 = 1;
+        const double d = t0 * P.e1[0] + t1 * P.e1[1] + t2 * P.e1[2];
+        w0 = t0 - d * P.e1[0]; w1 = t1 - d * P.e1[1]; w2 = t2 - d * P.e1[2];
+        const double n = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+        e2[0] = w0 / n; e2[1] = w1 / n; e2[2] = w2 / n;
+        b = 0.0;
+        return;
+    }
+    b = sqrt(b2);
+    const double ib = 1.0 / b;
+    e2[0] = w0 * ib; e2[1] = w1 * ib; e2[2] = w2 * ib;
+}
+
+// traceRay's setup (src/Raytracer.hs:69-75): ray, h2 = |pos x vel|^2, acc = 0
+BSB_HD void ray_init(const FrameParams &P, int x, int y, RayState &s)
+{
+    double dir[3], e2[3], a, b;
+    ray_direction(P, x, y, dir);
+    plane_basis(P, dir, a, b, e2);
+    // h2 exactly as the reference forms it (:73 quadrance (pos `cross` vel))
+    const double c0 = sub_rn(mul_rn(P.cam[1], dir[2]), mul_rn(P.cam[2], dir[1]));
+    const double c1 = sub_rn(mul_rn(P.cam[2], dir[0]), mul_rn(P.cam[0], dir[2]));
+    const double c2 = sub_rn(mul_rn(P.cam[0], dir[1]), mul_rn(P.cam[1], dir[0]));
+    const double h2 = add_rn(add_rn(mul_rn(c0, c0), mul_rn(c1, c1)), mul_rn(c2, c2));
+    s.u = P.r0; s.v = 0.0;
+    s.du = a;   s.dv = b;
+    s.q = P.q0;
+    s.y = P.cam[1];
+    s.k = -1.5 * h2;
+    s.e2y = e2[1];
+    s.acc[0] = s.acc[1] = s.acc[2] = s.acc[3] = 0.0;
+    s.steps = 0;
+    s.status = kAlive;
+}
+
+// signum class with Haskell's semantics for zeros: -1, 0, +1 (Raytracer.hs:96 compares signum y' /= signum y)
+BSB_HD int sign_class(double y) { return (y > 0.0) - (y < 0.0); }
+
+// massiv-io HSI -> RGB (see oracle/oracle_thirdparty.c for the statement of the formula)
+BSB_HD void hsi_to_rgb(double hp, double s, double i, double rgb[3])
+{
+    const double pi = 3.141592653589793;
+    const double h = hp * 2 * pi;
+    const double is = i * s;
+    const double second = i - is;
+    double r, g, b;
+    if (h < 0) {
+        r = g = b = NAN;
+    } else if (h < 2 * pi / 3) {
+        r = i + is * cos(h) / cos(pi / 3 - h);
+        b = second;
+        g = i + 2 * is + b - r;
+    } else if (h < 4 * pi / 3) {
+        g = i + is * cos(h - 2 * pi / 3) / cos(h + pi);
+        r = second;
+        b = i + 2 * is + r - g;
+    } else if (h < 2 * pi) {
+        b = i + is * cos(h - 4 * pi / 3) / cos(2 * pi - pi / 3 - h);
+        g = second;
+        r = i + 2 * is + g - b;
+    } else {
+        r = g = b = NAN;
+    }
+    rgb[0] = r; rgb[1] = g; rgb[2] = b;
+}
+
+// blend (src/Raytracer.hs:34-37): acc is on top, c goes below it; all four channels
+BSB_HD void blend_under(double acc[4], const double c[4])
+{
+    const double t = 1.0 - acc[3];
+    acc[0] = fma_(c[0], t, acc[0]);
+    acc[1] = fma_(c[1], t, acc[1]);
+    acc[2] = fma_(c[2], t, acc[2]);
+    acc[3] = fma_(c[3], t, acc[3]);
+}
+
+// diskColor' (src/Raytracer.hs:104-111)
+BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
+{
+    const double pi = 3.141592653589793;
+    const double r = sqrt(r2ave);
+    const double qn = (P.r_out - r) / (P.r_out - P.r_in);
+    const double intensity = sin(pi * (qn * qn));
+    const double c[4] = { P.disk_rgb[0] * intensity, P.disk_rgb[1] * intensity, P.disk_rgb[2] * intensity,
+                          intensity * P.disk_opacity };
+    blend_under(acc, c);
+}
+
+// Advance one ray by at most `max_steps` RK4 steps (colorize', src/Raytracer.hs:80-85).
+// The reference takes the step first and then tests the OLD position; testing first and
+// skipping the (unused) last step gives the same result with one step less per ray.
+BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
+{
+    double u = s.u, v = s.v, du = s.du, dv = s.dv, q = s.q, y = s.y;
+    const double k = s.k;
+    const double e1y = P.e1[1], e2y = s.e2y;
+    const bool disk = P.disk_opacity != 0.0;
+    uint32_t n = 0;
+    int32_t status = kAlive;
+    while (n < max_steps) {
+        if (q < 1.0) { status = kBlack; break; }                   // :93 passed the horizon
+        if (q > P.safe2) { status = kSky; break; }                 // :94 escaped
+        if (s.steps + n >= P.step_cap) { status = kCapped; break; }
+        // ---- classical RK4 on y' = f(y), f(vel,pos) = (k |pos|^-5 pos, vel)   (:113-134)
+        const double g1 = rinv5k(q, k);
+        const double a1u = g1 * u, a1v = g1 * v;
+        const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
+        const double g2 = rinv5k(fma_(p2u, p2u, p2v * p2v), k);
+        const double a2u = g2 * p2u, a2v = g2 * p2v;
+        const double p3u = fma_(P.hh2, a1u, p2u), p3v = fma_(P.hh2, a1v, p2v);
+        const double g3 = rinv5k(fma_(p3u, p3u, p3v * p3v), k);
+        const double a3u = g3 * p3u, a3v = g3 * p3v;
+        const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
+        const double p4u = fma_(P.hhh, a2u, peu), p4v = fma_(P.hhh, a2v, pev);
+        const double g4 = rinv5k(fma_(p4u, p4u, p4v * p4v), k);
+        const double a4u = g4 * p4u, a4v = g4 * p4v;
+        const double s23u = a2u + a3u, s23v = a2v + a3v;
+        const double nu = fma_(P.hsq6, a1u + s23u, peu);
+        const double nv = fma_(P.hsq6, a1v + s23v, pev);
+        du = fma_(P.h6, fma_(2.0, s23u, a1u) + a4u, du);
+        dv = fma_(P.h6, fma_(2.0, s23v, a1v) + a4v, dv);
+        const double nq = fma_(nu, nu, nv * nv);
+        const double ny = fma_(e1y, nu, e2y * nv);
+        n++;
+        // ---- disk crossing between the old and the new position (:96-98)
+        if (disk && sign_class(ny) != sign_class(y)) {
+            const double r2ave = (ny * q - y * nq) / (ny - y);      // :102
+            if (r2ave > P.din2 && r2ave < P.dout2) disk_layer(P, r2ave, s.acc);
+        }
+        u = nu; v = nv; q = nq; y = ny;
+    }
+    s.u = u; s.v = v; s.du = du; s.dv = dv; s.q = q; s.y = y;
+    s.steps += n;
+    s.status = status;
+}
+
+// ---- sky: StarMap.starLookup (src/StarMap.hs:93-115) over the bucketed k-d tree --------
+// `top` points at the tree's top levels (shared memory on the device), `n_top` nodes of it.
+BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, const double vel[3],
+                            double rgb[3])
+{
+    rgb[0] = rgb[1] = rgb[2] = 0.0;
+    const StarTreeDev &T = P.tree;
+    if (T.n_stars <= 0) return 0;  // empty KdMap: inRadius = [] -> PixelRGB 0 0 0
+    // :103 nvel = normalize vel
+    double n0, n1, n2;
+    {
+        const double l = add_rn(add_rn(mul_rn(vel[0], vel[0]), mul_rn(vel[1], vel[1])), mul_rn(vel[2], vel[2]));
+        if (fabs(l) <= 1e-12 || fabs(sub_rn(1.0, l)) <= 1e-12) {
+            n0 = vel[0]; n1 = vel[1]; n2 = vel[2];
+        } else {
+            const double sl = sqrt_rn(l);
+            n0 = div_rn(vel[0], sl); n1 = div_rn(vel[1], sl); n2 = div_rn(vel[2], sl);
+        }
+    }
+    const double w = 0.0005;                      // :101
+    const double radius = 3 * w;                  // :104
+    const double r2max = mul_rn(radius, radius);  // kdt: distSqr p q <= radius*radius
+    const double rprune = radius + 1e-12;         // split values carry the axis in 2 mantissa bits
+    const double a_mag = 0.013862943611198907;    // :108 log 2 / dynamic (= ln2/50, correctly rounded)
+    const double two_w2 = 2 * (w * w);            // :113 d2 / (2*w^2)
+    const int n_internal = (1 << T.depth) - 1;
+    uint32_t hits = 0;
+    int stack[24];
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+        while (node < n_internal) {
+            union { double d; uint64_t b; } sv;
+            sv.d = (node < n_top) ? top[node] : T.split[node];
+            const int axis = (int)(sv.b & 3ull);
+            const double qa = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+            const double diff = qa - sv.d;
+            const int near = 2 * node + 1 + (diff > 0.0 ? 1 : 0);
+            const int far = 2 * node + 1 + (diff > 0.0 ? 0 : 1);
+            if (fabs(diff) <= rprune) stack[sp++] = far;
+            node = near;
+        }
+        const int leaf = node - n_internal;
+        const uint32_t b0 = T.leaf_off[leaf], b1 = T.leaf_off[leaf + 1];
+        for (uint32_t j = b0; j < b1; j++) {
+            const StarRec &st = T.stars[j];
+            const double dx = sub_rn(st.x, n0), dy = sub_rn(st.y, n1), dz = sub_rn(st.z, n2);
+            const double d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)); // :107 qd
+            if (d2 <= r2max) {
+                const double ex = exp(a_mag * (950.0 - (double)st.mag) - d2 / two_w2);        // :113
+                const double val = (ex < 1.0 ? ex : 1.0) * P.star_intensity;                  // :112
+                double c[3];
+                hsi_to_rgb(st.hue, P.star_saturation * st.sat, val, c);                       // :114
+                rgb[0] += c[0]; rgb[1] += c[1]; rgb[2] += c[2];                               // :115 foldl'
+                hits++;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    rgb[0] = rgb[0] < 1.0 ? rgb[0] : 1.0;          // :115 fmap (min 1)
+    rgb[1] = rgb[1] < 1.0 ? rgb[1] : 1.0;
+    rgb[2] = rgb[2] < 1.0 ? rgb[2] : 1.0;
+    return hits;
+}
+
+// Finish a terminated ray: findColor's Bottom cases (src/Raytracer.hs:93-95) + dropAlpha (:75).
+// (x, y) are the ray's grid coordinates, needed to rebuild e2 for the 3-D exit velocity.
+BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, int x, int y,
+                           const RayState &s, double rgb[3])
+{
+    uint32_t hits = 0;
+    double acc[4] = { s.acc[0], s.acc[1], s.acc[2], s.acc[3] };
+    if (s.status == kSky) {
+        double c[4] = { 0, 0, 0, 1.0 };
+        if (P.tree.n_stars > 0) {
+            double dir[3], e2[3], a, b;
+            ray_direction(P, x, y, dir);
+            plane_basis(P, dir, a, b, e2);
+            const double vel[3] = { fma_(s.du, P.e1[0], s.dv * e2[0]), fma_(s.du, P.e1[1], s.dv * e2[1]),
+                                    fma_(s.du, P.e1[2], s.dv * e2[2]) };
+            hits = star_lookup(P, top, n_top, vel, c);
+        }
+        blend_under(acc, c);
+    }
+    // kBlack: blend (0,0,0,1) under acc leaves rgb unchanged; kCapped: whatever was accumulated
+    rgb[0] = acc[0]; rgb[1] = acc[1]; rgb[2] = acc[2];
+    return hits;
+}
+
+}  // namespace bsb

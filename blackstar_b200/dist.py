@@ -1,0 +1,85 @@
+"""One-process-per-GPU execution of the path (torchrun): row tiles + ONE gather.
+
+The reference's only parallelism is data-parallel over pixels inside one process
+(massiv ``Par``, src/Raytracer.hs:66).  Rays are independent, so the final image is cut
+into contiguous row tiles, rank k renders rows [H k/N, H (k+1)/N) with ``bsb_render_device``
+and the tiles are gathered on rank 0 with a single grouped NCCL send/recv over NVLink; bloom
+runs on rank 0 afterwards because its vertical reach (3 * (W div 25) rows) is about a whole
+tile at N = 8.  No other collective exists on this path.
+
+``torch`` is plumbing here (device memory, streams, ``torch.distributed``); the arithmetic
+is in libblackstar_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .config import Config
+
+
+def row_tiles(height: int, world: int) -> List[Tuple[int, int]]:
+    """Rows [H k/N, H (k+1)/N) for k = 0..N-1 (the same split bsb_render_full uses)."""
+    return [(height * k // world, height * (k + 1) // world) for k in range(world)]
+
+
+def gather_tiles(full: Optional[torch.Tensor], tile: Optional[torch.Tensor], tiles: List[Tuple[int, int]],
+                 rank: int, world: int, group=None) -> None:
+    """Gather row tiles into ``full`` (H x W x C) on rank 0.  Rank 0's own tile must already
+    be in place (it renders straight into ``full``).  One grouped send/recv: with the NCCL
+    backend this is the path's single collective; with gloo (CPU tests) the same calls work."""
+    if world == 1:
+        return
+    ops = []
+    if rank == 0:
+        for k in range(1, world):
+            r0, r1 = tiles[k]
+            if r1 > r0:
+                ops.append(dist.P2POp(dist.irecv, full[r0:r1], k, group))
+    else:
+        r0, r1 = tiles[rank]
+        if r1 > r0:
+            ops.append(dist.P2POp(dist.isend, tile, 0, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class TiledFrame:
+    """Per-rank state for rendering one scene across the ranks of a process group.
+
+    ``step()`` = Main.doRender's device work for one frame: trace my tile, gather on rank 0,
+    bloom on rank 0 (iff bloomStrength /= 0).  The result stays in HBM (``self.full`` on
+    rank 0).  ``step_to_host(out)`` additionally copies it into a pinned host tensor.
+    """
+
+    def __init__(self, renderer, cfg: Config, rank: int, world: int, device: torch.device):
+        self.r, self.cfg, self.rank, self.world, self.device = renderer, cfg, rank, world, device
+        W, H = cfg.scene.resolution
+        self.W, self.H = W, H
+        self.tiles = row_tiles(H, world)
+        r0, r1 = self.tiles[rank]
+        self.full = torch.empty((H, W, 4), dtype=torch.float32, device=device) if rank == 0 else None
+        self.tile = self.full[r0:r1] if rank == 0 else torch.empty((r1 - r0, W, 4), dtype=torch.float32, device=device)
+        self.launches = 0
+        # run the library's kernels on torch's current stream so they order with the NCCL ops
+        self.r.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def step(self, want_stats: bool = False):
+        r0, r1 = self.tiles[self.rank]
+        st = self.r.render_device(self.cfg, self.tile.data_ptr(), r0, r1, want_stats=want_stats)
+        self.launches += 1 if r1 > r0 else 0
+        gather_tiles(self.full, self.tile, self.tiles, self.rank, self.world)
+        scn = self.cfg.scene
+        if self.rank == 0 and scn.bloomStrength != 0:  # app/Main.hs:113
+            self.r.bloom_device(scn.bloomStrength, scn.bloomDivider, self.W, self.H, self.full.data_ptr(),
+                                self.full.data_ptr())
+            self.launches += 2
+        return st
+
+    def step_to_host(self, host_out: Optional[torch.Tensor]):
+        self.step()
+        if self.rank == 0:
+            host_out.copy_(self.full, non_blocking=True)

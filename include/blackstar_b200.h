@@ -106,6 +106,10 @@ const char *bsb_version(void);
  * NULL restores the ctx's stream. */
 int bsb_set_stream(bsb_ctx *ctx, void *cuda_stream);
 
+/* Tuning knobs.  "trace_variant": 0 = one tile of 32 rays per warp, 1..3 = persistent warps
+ * with ballot compaction (step block 16/8/32).  Same arithmetic, same image. */
+int bsb_set_option(bsb_ctx *ctx, const char *key, double value);
+
 /* ---- star map: replaces StarMap.readTreeFromFile + the StarTree argument --------------
  * (src/StarMap.hs:82-85, src/Raytracer.hs:53).  The flat star list is copied, a
  * bucketed k-d tree is built on the host and uploaded once to every GPU of the ctx.
@@ -153,6 +157,12 @@ int bsb_render_full_srgb8(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *
 int bsb_measure_fp64_peak(bsb_ctx *ctx, double *tflops);
 /* device-to-device copy of `bytes` bytes, best of `reps`: returns GB/s (read+write). */
 int bsb_measure_hbm_copy(bsb_ctx *ctx, size_t bytes, int reps, double *gbs);
+
+/* Numerics self-test of the geodesic kernel's |pos|^-5 primitive (MUFU.RSQ64H seed +
+ * third-order correction): max relative error against pow(q, -2.5) and the largest seed
+ * residual |1 - q*y0^2| over n log-spaced q in [q_lo, q_hi]. */
+int bsb_selftest_rinv5(bsb_ctx *ctx, double q_lo, double q_hi, int n, double *max_rel_err,
+                       double *max_seed_residual);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,94 @@
+// hostcheck.cpp -- TEST-ONLY harness: instantiates blackstar_b200/csrc/trace_core.cuh (the
+// exact per-ray arithmetic the sm_100a kernels inline) for the HOST so that tests can diff
+// it against the oracle in a container without a GPU.  Never linked into
+// libblackstar_b200.so; the product has no CPU path.
+#include "../../blackstar_b200/csrc/host_setup.hpp"
+#include "../../blackstar_b200/csrc/trace_core.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace bsb;
+
+struct HcCtx {
+    HostStarTree tree;
+    size_t n = 0;
+};
+
+extern "C" {
+
+void *hc_create(const bsb_star *stars, size_t n, int leaf_size)
+{
+    HcCtx *c = new HcCtx();
+    c->n = n;
+    if (n) build_star_tree(stars, n, leaf_size, c->tree);
+    return c;
+}
+
+void hc_destroy(void *p) { delete static_cast<HcCtx *>(p); }
+
+int hc_tree_depth(void *p) { return static_cast<HcCtx *>(p)->tree.depth; }
+
+static void attach(HcCtx *c, FrameParams &P)
+{
+    P.tree.split = c->tree.split.data();
+    P.tree.leaf_off = c->tree.leaf_off.data();
+    P.tree.stars = c->tree.stars.data();
+    P.tree.depth = c->tree.depth;
+    P.tree.n_stars = (int)c->n;
+}
+
+// Renders rows [row0,row1) of the final image exactly as the tiles kernel does per lane.
+// block_steps > 0 advances in blocks (the refill kernel's schedule) instead of one call.
+int hc_render(void *p, const bsb_camera *cam, const bsb_scene *scn, int row0, int row1, int block_steps,
+              double *out_rgb, unsigned long long *steps_out, unsigned long long *hits_out)
+{
+    HcCtx *c = static_cast<HcCtx *>(p);
+    FrameParams P;
+    if (!make_frame_params(*cam, *scn, row0, row1, P).empty()) return 1;
+    attach(c, P);
+    const int n_internal = (1 << P.tree.depth) - 1;
+    const int n_top = c->n ? (n_internal < kSmemTreeNodes ? n_internal : kSmemTreeNodes) : 0;
+    unsigned long long steps = 0, hits = 0;
+    for (int oy = row0; oy < row1; oy++)
+        for (int ox = 0; ox < P.W; ox++) {
+            double px[4][3];
+            const int nsub = P.ss ? 4 : 1;
+            for (int sub = 0; sub < nsub; sub++) {
+                const int gx = P.ss ? 2 * ox + (sub >> 1) : ox;
+                const int gy = P.ss ? 2 * oy + (sub & 1) : oy;
+                RayState s;
+                ray_init(P, gx, gy, s);
+                if (block_steps > 0) {
+                    while (s.status == kAlive) ray_advance(P, s, (uint32_t)block_steps);
+                } else {
+                    ray_advance(P, s, 0xffffffffu);
+                }
+                hits += ray_finish(P, P.tree.split, n_top, gx, gy, s, px[sub]);
+                steps += s.steps;
+            }
+            double *o = out_rgb + ((size_t)(oy - row0) * P.W + ox) * 3;
+            for (int k = 0; k < 3; k++)
+                o[k] = P.ss ? 0.25 * (((px[0][k] + px[1][k]) + px[2][k]) + px[3][k]) : px[0][k];
+        }
+    if (steps_out) *steps_out = steps;
+    if (hits_out) *hits_out = hits;
+    return 0;
+}
+
+void hc_star_lookup(void *p, double intensity, double saturation, const double vel[3], double rgb[3], unsigned *hits)
+{
+    HcCtx *c = static_cast<HcCtx *>(p);
+    FrameParams P;
+    std::memset(&P, 0, sizeof P);
+    attach(c, P);
+    P.star_intensity = intensity;
+    P.star_saturation = saturation;
+    const int n_internal = (1 << P.tree.depth) - 1;
+    const int n_top = c->n ? (n_internal < kSmemTreeNodes ? n_internal : kSmemTreeNodes) : 0;
+    *hits = star_lookup(P, P.tree.split, n_top, vel, rgb);
+}
+
+double hc_rinv5k(double q, double k) { return rinv5k(q, k); }
+
+}  // extern "C"

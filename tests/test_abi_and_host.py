@@ -1,0 +1,107 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol (no compute without
+a GPU), and the host-side mirror of ConfigFile.hs / Main.prepareScene / StarMap.readMap."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from blackstar_b200 import _lib, config, starmap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "blackstar_b200.h")).read()
+    declared = set(re.findall(r"\b(bsb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"bsb_ctx"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    L.bsb_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.bsb_version()
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(config.CCamera) == 80
+    assert ctypes.sizeof(config.CScene) == 96
+    assert ctypes.sizeof(_lib.CStats) == 80
+    assert starmap.STAR_DTYPE.itemsize == 48
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _lib.load()
+    assert not L.bsb_create(1)
+    msg = L.bsb_last_error(None).decode()
+    assert "no CPU fallback" in msg or "CUDA" in msg
+    from blackstar_b200.render import Renderer
+    with pytest.raises(_lib.BlackstarError):
+        Renderer()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "blackstar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in src and "liboracle" not in src and "blackstar_oracle" not in src, f
+
+
+def test_yaml_defaults(tmp_path):
+    p = tmp_path / "s.yaml"
+    p.write_text("camera: {position: [1,2,3], lookAt: [0,0,0], upVec: [0,1,0], fov: 1.0}\nscene: {}\n")
+    cfg = config.load_config(str(p))
+    s = cfg.scene  # src/ConfigFile.hs:68-79
+    assert (s.stepSize, s.bloomStrength, s.bloomDivider, s.starIntensity, s.starSaturation) == (0.3, 0.4, 25, 0.7, 0.7)
+    assert s.diskColor == (0.16, 0.1, 0.95) and s.diskOpacity == 0 and (s.diskInner, s.diskOuter) == (3, 12)
+    assert s.resolution == (1280, 720) and s.supersampling is False
+
+
+def test_hue_is_divided_by_360_and_unknown_keys_ignored(scenes_dir):
+    cfg = config.load_config(f"{scenes_dir}/default.yaml")
+    assert cfg.scene.diskColor == (0.5, 0.1, 1.05)
+    d = {"camera": {"position": [0, 0, 1], "lookAt": [0, 0, 0], "upVec": [0, 1, 0], "fov": 1},
+         "scene": {"diskHSV": [180, 0.1, 1.05]}}
+    assert config.config_from_dict(d).scene.diskColor == (0.16, 0.1, 0.95)  # S10: diskHSV is not a key
+    with pytest.raises(ValueError):
+        config.config_from_dict({"scene": {}})
+    with pytest.raises(ValueError):
+        config.config_from_dict({"scene": {}, "camera": {"position": [0, 0, 1]}})
+
+
+def test_preview_override(scenes_dir):
+    cfg = config.prepare_scene(config.load_config(f"{scenes_dir}/default-aa.yaml"), True)
+    assert cfg.scene.resolution == (300, 168) and not cfg.scene.supersampling and cfg.scene.bloomStrength == 0
+    tall = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 600, 800)
+    assert config.prepare_scene(tall, True).scene.resolution == (225, 300)
+    assert config.prepare_scene(tall, False) is tall
+
+
+def test_all_scenes_load(scenes_dir):
+    names = sorted(f for f in os.listdir(scenes_dir) if f.endswith(".yaml"))
+    assert len(names) == 9
+    for n in names:
+        cfg = config.load_config(os.path.join(scenes_dir, n))
+        cam, scn = config.to_c(cfg)
+        assert scn.width == cfg.scene.resolution[0] and cam.fov == cfg.camera.fov
+
+
+def test_synthetic_catalogue_is_deterministic_and_well_formed():
+    a = starmap.synthetic_catalogue(1000, seed=starmap.DEFAULT_SEED)
+    b = starmap.synthetic_catalogue(1000, seed=starmap.DEFAULT_SEED)
+    assert a == b and len(a) == 28 + 28 * 1000
+    s = starmap.read_ppm(a)
+    np.testing.assert_allclose(np.linalg.norm(s["pos"], axis=1), 1.0, atol=1e-15)
+    assert s["mag"].min() >= -150 and s["mag"].max() <= 1300
+    assert set(np.unique(s["hue"])) <= {0.0, 0.631, 0.628, 0.622, 0.650, 0.089, 0.094}
+    # pinned first record so a change of generator cannot pass unnoticed
+    full = starmap.synthetic_catalogue(3, seed=starmap.DEFAULT_SEED)
+    assert full[28:36].hex() == starmap.synthetic_catalogue(1, seed=starmap.DEFAULT_SEED)[28:36].hex()
+    with pytest.raises(ValueError):
+        starmap.read_ppm(b"short")

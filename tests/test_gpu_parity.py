@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the
+committed golden fixtures.  Tolerance (north_star): per-channel max-abs error < 1e-4 on the
+linear float framebuffer; integer/byte outputs (sRGB8) bit-exact."""
+import ctypes
+import dataclasses
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden  # noqa: E402
+
+from blackstar_b200 import _lib, config, starmap  # noqa: E402
+from blackstar_b200.render import Renderer  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+TOL = 1e-4
+SCENES = ["closeup", "default", "default-aa", "fartheraway", "lensing-disk", "lensing", "wideangle-disk",
+          "wideangle", "wideangle1"]
+
+
+@pytest.fixture(scope="module")
+def rnd():
+    r = Renderer(devices=[0])   # raises (no fallback) if the .so or the GPU is missing
+    yield r
+    r.close()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "scenes_48.npz"))
+
+
+@pytest.fixture(scope="module")
+def stars40k():
+    return starmap.synthetic_stars(40000, seed=5)
+
+
+def rgb(img):
+    return img[..., :3].astype(np.float64)
+
+
+def test_rinv5_primitive_on_device(rnd):
+    rel, seed = rnd.selftest_rinv5(0.25, 1e5, 1 << 20)
+    print(f"rinv5k max rel err {rel:.3e}; MUFU.RSQ64H seed residual {seed:.3e} (2^{np.log2(seed):.1f})")
+    assert rel < 2e-15          # ~ a few ulp of double
+    assert seed < 2.0 ** -17    # the correction polynomial is designed for |e| <~ 2^-19
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_golden_scenes(rnd, golden, scenes_dir, scene):
+    cfg = make_golden.golden_config(f"{scenes_dir}/{scene}.yaml")
+    rnd.set_stars(starmap.synthetic_stars(**make_golden.GOLDEN_STARS))
+    rnd.set_option("trace_variant", 0)
+    img = rnd.render(cfg)
+    st = rnd.last_stats
+    nrays = img.shape[0] * img.shape[1] * (4 if cfg.scene.supersampling else 1)
+    assert np.abs(rgb(img) - golden[scene + "/render"]).max() < TOL
+    assert (img[..., 3] == 1).all()
+    assert st["rays"] == nrays and st["capped"] == 0
+    assert st["steps"] == int(golden[scene + "/steps"][0]) - nrays  # the unused last RK4 of each ray is skipped
+    full = rnd.do_render(cfg)
+    assert np.abs(rgb(full) - golden[scene + "/bloomed"]).max() < TOL
+    u8 = rnd.do_render_srgb8(cfg)
+    diff = np.abs(u8.astype(int) - golden[scene + "/srgb8"].astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 2e-3  # float32 framebuffer vs f64: rare 1-LSB flips
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_scene_vs_oracle_all_schedules(rnd, scenes_dir, stars40k, scene):
+    cfg = config.load_config(f"{scenes_dir}/{scene}.yaml")
+    w, h = cfg.scene.resolution
+    cfg = config.with_resolution(cfg, 136, 136 * h // w + 1)   # odd sizes exercise tile padding
+    rnd.set_stars(stars40k)
+    ref, rsteps = po.render(cfg, po.Tree(stars40k))
+    imgs = []
+    for variant in (0, 1, 2, 3):
+        rnd.set_option("trace_variant", variant)
+        img = rnd.render(cfg)
+        assert np.abs(rgb(img) - ref).max() < TOL, f"variant {variant}"
+        nrays = img.shape[0] * img.shape[1] * (4 if cfg.scene.supersampling else 1)
+        assert rnd.last_stats["steps"] == rsteps - nrays, f"variant {variant}"
+        imgs.append(img)
+    rnd.set_option("trace_variant", 0)
+    for im in imgs[1:]:
+        np.testing.assert_array_equal(im, imgs[0])  # schedules differ, arithmetic does not
+
+
+def test_row_tiles_concatenate_bit_exactly(rnd, scenes_dir, stars40k):
+    # multi-GPU correctness without a cluster: N row-tile renders == 1 render
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default-aa.yaml"), 200, 113)
+    rnd.set_stars(stars40k)
+    whole = rnd.render(cfg)
+    for n in (2, 3, 8):
+        H = 113
+        parts = [rnd.render(cfg, H * k // n, H * (k + 1) // n) for k in range(n)]
+        np.testing.assert_array_equal(np.concatenate(parts, axis=0), whole)
+    assert rnd.render(cfg, 5, 5).shape == (0, 200, 4)  # empty tile is legal
+
+
+def test_empty_star_map_is_black_sky(rnd, scenes_dir):
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 160, 90)
+    rnd.set_stars(None)
+    assert rnd.star_count == 0
+    img = rnd.render(cfg)
+    ref, _ = po.render(cfg, None)
+    assert np.abs(rgb(img) - ref).max() < TOL
+    assert rnd.last_stats["star_hits"] == 0
+
+
+def test_ppm_ingestion_equals_flat_list(rnd, scenes_dir):
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/wideangle1.yaml"), 128, 72)
+    data = starmap.synthetic_catalogue(50000, seed=21)
+    rnd.set_stars_ppm(data)
+    assert rnd.star_count == 50000
+    a = rnd.render(cfg)
+    rnd.set_stars(starmap.read_ppm(data))
+    b = rnd.render(cfg)
+    assert np.abs(a - b).max() < 1e-6   # libm vs numpy cos/sin may differ by an ulp in star positions
+    with pytest.raises(_lib.BlackstarError):
+        rnd.set_stars_ppm(b"tiny")
+
+
+@pytest.mark.parametrize("shape,divider", [((40, 64), 25), ((64, 40), 7), ((300, 500), 25), ((270, 480), 3),
+                                           ((90, 1300), 25), ((1100, 70), 2), ((33, 2500), 25), ((17, 4100), 25),
+                                           ((4100, 26), 25)])
+def test_bloom_vs_oracle(rnd, shape, divider):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    H, W = shape
+    img = np.zeros((H, W, 4), dtype=np.float32)
+    img[..., :3] = rng.uniform(0, 1.2, (H, W, 3)).astype(np.float32)
+    img[..., 3] = 1
+    img[rng.integers(H), rng.integers(W), :3] = 50.0  # a hot pixel (stars/disk produce these)
+    got = rnd.bloom(0.4, divider, img)
+    ref = po.bloom(0.4, divider, rgb(img))
+    assert np.abs(rgb(got) - ref).max() < 1e-5
+    assert (got[..., 3] == 1).all()
+
+
+def test_bloom_error_behaviour(rnd):
+    img = np.ones((8, 10, 4), dtype=np.float32)
+    with pytest.raises(_lib.BlackstarError) as e:
+        rnd.bloom(0.4, 25, img)     # r = 10 div 25 = 0: the reference's boxBlur crashes (foldl1' [])
+    assert e.value.code == 1
+    with pytest.raises(_lib.BlackstarError):
+        rnd.bloom(0.4, 0, img)
+
+
+def test_srgb8_bit_exact(rnd):
+    rng = np.random.default_rng(5)
+    img = np.ones((37, 53, 4), dtype=np.float32)
+    img[..., :3] = rng.uniform(-0.1, 1.3, (37, 53, 3)).astype(np.float32)
+    img[0, 0, :3] = [0.0, 0.0031308, 1.0]
+    got = rnd.to_srgb8(img)
+    ref = po.to_srgb8(rgb(img))
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_invalid_arguments_return_status_not_crash(rnd, scenes_dir):
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 32, 18)
+    with pytest.raises(_lib.BlackstarError):
+        rnd.render(cfg, 3, 99)
+    bad = config.Config(scene=dataclasses.replace(cfg.scene, stepSize=0.0), camera=cfg.camera)
+    with pytest.raises(_lib.BlackstarError):
+        rnd.render(bad)
+    bad = config.Config(scene=cfg.scene, camera=dataclasses.replace(cfg.camera, fov=float("nan")))
+    with pytest.raises(_lib.BlackstarError):
+        rnd.render(bad)
+    with pytest.raises(_lib.BlackstarError):
+        rnd.set_option("no_such_option", 1)
+    # the ctx is still usable afterwards
+    assert rnd.render(cfg).shape == (18, 32, 4)
+
+
+def test_camera_inside_horizon_and_radial_ray(rnd, scenes_dir):
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 16, 16)
+    rnd.set_stars(None)
+    inside = config.Config(scene=cfg.scene, camera=dataclasses.replace(cfg.camera, position=(0.3, 0.2, 0.1)))
+    assert (rnd.render(inside)[..., :3] == 0).all()
+    radial = config.Config(scene=dataclasses.replace(cfg.scene, resolution=(2, 2)),
+                           camera=dataclasses.replace(cfg.camera, lookAt=(0.0, 0.0, 0.0)))
+    img = rnd.render(radial)
+    ref, _ = po.render(radial, None)
+    assert np.abs(rgb(img) - ref).max() < TOL
+
+
+def test_full_size_rows_default_1080p(rnd, scenes_dir):
+    # BASELINE config 2: default.yaml 1920x1080, no star map.  Oracle on a band of rows.
+    cfg = config.load_config(f"{scenes_dir}/default.yaml")
+    rnd.set_stars(None)
+    whole = rnd.render(cfg)
+    assert whole.shape == (1080, 1920, 4) and np.isfinite(whole).all()
+    for r0 in (0, 537, 1076):
+        ref, _ = po.render(cfg, None, r0, r0 + 4)
+        assert np.abs(rgb(whole[r0:r0 + 4]) - ref).max() < TOL
+    # idempotence: same call, same bits
+    np.testing.assert_array_equal(rnd.render(cfg), whole)
+
+
+def test_full_size_rows_default_aa_4096(rnd, scenes_dir):
+    # BASELINE config 3 (headline): default-aa.yaml at 4096x4096 with x4 supersampling + stars + bloom
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default-aa.yaml"), 4096, 4096)
+    stars = starmap.synthetic_stars()  # N = 468 861, seed 20190412
+    rnd.set_stars(stars)
+    tree = po.Tree(stars)
+    for variant in (0, 1):
+        rnd.set_option("trace_variant", variant)
+        for r0 in (1000, 2046):
+            band = rnd.render(cfg, r0, r0 + 2)
+            ref, _ = po.render(cfg, tree, r0, r0 + 2)
+            assert np.abs(rgb(band) - ref).max() < TOL
+    rnd.set_option("trace_variant", 0)
+    full = rnd.do_render(cfg)   # render + bloom at full size
+    st = rnd.last_stats
+    assert st["rays"] == 4 * 4096 * 4096 and st["capped"] == 0
+    assert np.isfinite(full).all()
+    # bloom is linear with non-negative weights: out >= img, and DC gain <= strength*(2r/(2r+1))^6
+    pre = rnd.render(cfg, 2046, 2050)
+    assert (rgb(full[2046:2050]) >= rgb(pre) - 1e-6).all()

@@ -1,0 +1,114 @@
+"""CPU tests of the KERNEL ARITHMETIC: blackstar_b200/csrc/trace_core.cuh (the code the
+sm_100a kernels inline: planar RK4, MUFU-seeded |pos|^-5, disk crossing, bucketed k-d tree
+lookup) is instantiated for the host by tests/hostcheck and diffed against the oracle.
+This is a development aid; the parity tests proper run on the GPU (test_gpu_parity.py)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from blackstar_b200 import config, starmap
+from oracle import pyoracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-4  # north_star: per-channel max-abs error on the linear framebuffer
+
+
+@pytest.fixture(scope="module")
+def hc():
+    subprocess.run(["make", "-C", os.path.join(HERE, "hostcheck")], check=True, capture_output=True)
+    L = ctypes.CDLL(os.path.join(HERE, "hostcheck", "libhostcheck.so"))
+    L.hc_create.restype = ctypes.c_void_p
+    L.hc_create.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    L.hc_destroy.argtypes = [ctypes.c_void_p]
+    L.hc_tree_depth.argtypes = [ctypes.c_void_p]
+    L.hc_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                            ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+    L.hc_star_lookup.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.POINTER(ctypes.c_uint)]
+    L.hc_rinv5k.restype = ctypes.c_double
+    L.hc_rinv5k.argtypes = [ctypes.c_double, ctypes.c_double]
+    return L
+
+
+def _hc_render(L, h, cfg, block=0):
+    W, H = cfg.scene.resolution
+    cam, scn = config.to_c(cfg)
+    out = np.zeros((H, W, 3))
+    st, hits = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    assert L.hc_render(h, ctypes.byref(cam), ctypes.byref(scn), 0, H, block, out.ctypes.data, ctypes.byref(st), ctypes.byref(hits)) == 0
+    return out, st.value, hits.value
+
+
+def test_rinv5k_is_full_double_precision(hc):
+    rng = np.random.default_rng(0)
+    q = np.exp(rng.uniform(np.log(0.25), np.log(1e5), 20000))
+    err = max(abs(hc.hc_rinv5k(float(x), -3.0) / (-3.0 * x ** -2.5) - 1) for x in q)
+    assert err < 1e-15
+
+
+@pytest.mark.parametrize("scene", ["closeup", "default", "default-aa", "fartheraway", "lensing-disk", "lensing",
+                                   "wideangle-disk", "wideangle", "wideangle1"])
+def test_every_scene_matches_oracle(hc, scenes_dir, scene):
+    cfg = config.load_config(f"{scenes_dir}/{scene}.yaml")
+    w, h = cfg.scene.resolution
+    cfg = config.with_resolution(cfg, 64, max(8, 64 * h // w))
+    stars = starmap.synthetic_stars(40000, seed=5)
+    tree = po.Tree(stars)
+    ref, rsteps = po.render(cfg, tree)
+    h_ = hc.hc_create(stars.ctypes.data, len(stars), 8)
+    try:
+        got, steps, _ = _hc_render(hc, h_, cfg)
+        got_blocked, steps_b, _ = _hc_render(hc, h_, cfg, block=16)
+    finally:
+        hc.hc_destroy(h_)
+    nrays = ref.shape[0] * ref.shape[1] * (4 if cfg.scene.supersampling else 1)
+    assert np.abs(got - ref).max() < TOL
+    # the kernel skips the reference's last (unused) RK4 evaluation of every ray
+    assert steps == rsteps - nrays
+    np.testing.assert_array_equal(got, got_blocked)  # step blocks do not change the arithmetic
+    assert steps_b == steps
+
+
+def test_star_lookup_matches_oracle_and_brute_force(hc, small_stars):
+    tree = po.Tree(small_stars)
+    rng = np.random.default_rng(4)
+    for leaf in (1, 8, 64):
+        h_ = hc.hc_create(small_stars.ctypes.data, len(small_stars), leaf)
+        try:
+            nonzero = 0
+            for k in range(400):
+                if k % 2:
+                    v = small_stars["pos"][rng.integers(len(small_stars))] + rng.normal(0, 0.0007, 3)
+                else:
+                    v = rng.normal(0, 1, 3)
+                v = np.ascontiguousarray(v * rng.uniform(0.5, 2.0))  # lookup normalises (StarMap.hs:103)
+                got = np.zeros(3)
+                hits = ctypes.c_uint()
+                hc.hc_star_lookup(h_, 0.7, 1.3, v.ctypes.data, got.ctypes.data, ctypes.byref(hits))
+                want = tree.lookup(0.7, 1.3, v)
+                n = v / np.linalg.norm(v)
+                d = small_stars["pos"] - n
+                d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+                assert hits.value == int((d2 <= 0.0015 * 0.0015).sum())
+                np.testing.assert_allclose(got, want, atol=1e-13)
+                nonzero += hits.value > 0
+            assert nonzero > 100
+        finally:
+            hc.hc_destroy(h_)
+
+
+def test_tiny_and_empty_catalogues(hc, scenes_dir):
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 32, 18)
+    ref0, _ = po.render(cfg, None)
+    for n in (0, 1, 5, 9):
+        stars = starmap.synthetic_stars(n, seed=9) if n else np.zeros(0, dtype=starmap.STAR_DTYPE)
+        h_ = hc.hc_create(stars.ctypes.data if n else None, n, 8)
+        try:
+            got, _, hits = _hc_render(hc, h_, cfg)
+        finally:
+            hc.hc_destroy(h_)
+        ref = ref0 if n == 0 else po.render(cfg, po.Tree(stars))[0]
+        assert np.abs(got - ref).max() < 1e-12
