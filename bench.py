@@ -110,24 +110,40 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU leg
-def cpu_sample(cfg, stars, seconds, threads=0):
-    """Time the C port of the reference (oracle) on a band of rows of the SAME frame, sized to
-    ~`seconds` of wall time on all host threads.  Returns (Mrays/s, description, rays, secs)."""
-    from oracle import pyoracle as po
-    tree = po.Tree(stars)
-    W, H = cfg.scene.resolution
-    ss = 4 if cfg.scene.supersampling else 1
-    mid = H // 2
-    t = time.perf_counter()
-    po.render(cfg, tree, mid, mid + 1, nthreads=threads)          # calibration: one row
-    per_row = max(time.perf_counter() - t, 1e-4)
-    rows = int(max(2, min(H, seconds / per_row)))
-    r0 = max(0, mid - rows // 2)
-    t = time.perf_counter()
-    _, steps = po.render(cfg, tree, r0, r0 + rows, nthreads=threads)
-    dt = time.perf_counter() - t
-    rays = rows * W * ss
-    return rays / dt / 1e6, f"rows [{r0},{r0 + rows}) of the {W}x{H} frame ({rays} rays, {steps} RK4 steps, {dt:.1f} s)", rays, dt
+class CpuArm:
+    """The C port of the reference (oracle) on a band of rows of the SAME frame, all host
+    threads (pthreads over rows, dynamic scheduling = massiv's Par on -N capabilities)."""
+
+    def __init__(self, cfg, stars, threads=0):
+        from oracle import pyoracle as po
+        self.po, self.cfg, self.threads = po, cfg, threads
+        self.tree = po.Tree(stars)
+        self.W, self.H = cfg.scene.resolution
+        self.ss = 4 if cfg.scene.supersampling else 1
+        self.cores = threads if threads > 0 else (os.cpu_count() or 1)
+        self.per_row = None
+
+    def calibrate(self):
+        cal = min(self.H, max(2, 2 * self.cores))                 # 2 rows per thread
+        c0 = max(0, self.H // 2 - cal // 2)
+        t = time.perf_counter()
+        self.po.render(self.cfg, self.tree, c0, c0 + cal, nthreads=self.threads)
+        self.per_row = max(time.perf_counter() - t, 1e-4) / cal
+        self.cal = cal
+
+    def sample(self, seconds):
+        """Returns (Mrays/s, description, rays, secs) for a band sized to ~`seconds`."""
+        if self.per_row is None:
+            self.calibrate()
+        rows = int(max(self.cal, min(self.H, seconds / self.per_row)))
+        r0 = max(0, self.H // 2 - rows // 2)
+        t = time.perf_counter()
+        _, steps = self.po.render(self.cfg, self.tree, r0, r0 + rows, nthreads=self.threads)
+        dt = time.perf_counter() - t
+        rays = rows * self.W * self.ss
+        desc = (f"rows [{r0},{r0 + rows}) of the {self.W}x{self.H} frame ({rays} rays, {steps} RK4 steps, "
+                f"{dt:.1f} s, {self.cores} threads)")
+        return rays / dt / 1e6, desc, rays, dt
 
 
 def run_reference(args):
@@ -136,13 +152,12 @@ def run_reference(args):
         return 0
     from blackstar_b200 import starmap
     cfg = load_workload(args.res)
-    stars = starmap.synthetic_stars()
-    cores = os.cpu_count() or 1
+    arm = CpuArm(cfg, starmap.synthetic_stars())
     total = args.steps + args.warmup
-    per_step = max(2.0, min(20.0, 150.0 / max(1, total)))
+    per_step = max(1.0, min(20.0, 150.0 / max(1, total)))
     vals, last = [], None
     for i in range(total):
-        v, desc, rays, dt = cpu_sample(cfg, stars, per_step)
+        v, desc, rays, dt = arm.sample(per_step)
         if i >= args.warmup:
             vals.append((rays, dt))
         last = desc
@@ -156,7 +171,7 @@ def run_reference(args):
                                "synthetic catalogue); each step = a bounded band of rows of that frame, no bloom",
                    "note": "GHC/stack are not installed here: this is the C port of the reference "
                            "(oracle/, gcc -O2 -ffp-contract=off, pthreads over rows), not the Haskell binary"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": last},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": arm.cores, "kind": "port", "sample": last},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -285,8 +300,9 @@ def run_b200(args):
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, desc, _, _ = cpu_sample(cfg, stars, args.cpu_seconds)
-        cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
+        arm = CpuArm(cfg, stars)
+        v, desc, _, _ = arm.sample(args.cpu_seconds)
+        cpu = {"value": v, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
                "sample": desc + "; C port of the reference (GHC unavailable), all host threads"}
 
     if rank == 0:

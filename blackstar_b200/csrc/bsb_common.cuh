@@ -62,6 +62,8 @@ struct FrameParams {
     double r_in, r_out;       // sqrt of din2, dout2 (diskColor' recomputes them per hit)
     double disk_rgb[3];
     double disk_opacity;
+    int32_t disk_on;          // disk_opacity != 0 (src/Raytracer.hs:96)
+    int32_t pad0_;
     // sky: src/StarMap.hs:93-115
     double star_intensity, star_saturation;
     StarTreeDev tree;

@@ -84,6 +84,7 @@ std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int r
     if (scn.disk_opacity != 0 && !(std::isfinite(P.disk_rgb[0])))
         return "diskColor hue outside [0, 360)";  // massiv-io raises `error` here
     P.disk_opacity = scn.disk_opacity;
+    P.disk_on = scn.disk_opacity != 0 ? 1 : 0;
     P.star_intensity = scn.star_intensity;
     P.star_saturation = scn.star_saturation;
     P.ss = scn.supersampling ? 1 : 0;

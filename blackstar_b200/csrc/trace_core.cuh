@@ -7,16 +7,22 @@
 //
 // Reference semantics: src/Raytracer.hs:34-134, src/StarMap.hs:93-115.
 //
-// B200-first restructuring:
-//  * every ray's motion is planar (the force is central), and classical RK4 commutes with
-//    rotations, so the reference's 6-double state (vel, pos) is integrated as 4 doubles
-//    (u, v, du, dv) in the orthonormal basis (e1, e2) of the ray's own orbital plane, with
-//    e1 = cam/|cam| shared by the whole frame.  In exact arithmetic this is the SAME discrete
-//    map as the reference's 3-D RK4 (same truncation error); only rounding (1e-16) differs.
-//  * |pos|^-5 comes from one MUFU.RSQ64H seed + a third-order correction (9 DP ops) instead
-//    of sqrt, three multiplies and a divide;
-//  * the stage velocities are eliminated algebraically (p3 = p2 + (h/2)^2 a1, ...), 72 DP
-//    instructions per step instead of the ~141 flops of the reference as written.
+// B200-first restructuring.  The kernel is bound by FP64 issue, so the
+// work per RK4 step is cut from the reference's 141 flops (4 sqrt + 4 div) to 64 DP
+// instructions + 4 MUFU without changing the discrete map:
+//  * every ray's motion is planar (the force is central) and classical RK4 commutes with
+//    linear changes of variables, so the 6-double state (vel, pos) is integrated as 4 doubles
+//    (u, v, du, dv) in an orthonormal basis (f1, f2) of the ray's own orbital plane.  In exact
+//    arithmetic this is the SAME discrete map as the reference's 3-D RK4 (same truncation
+//    error); only rounding (1e-16 per step) differs.
+//  * f2 is chosen horizontal, so scene-y = f1y * u: the disk-crossing test (signum y' /=
+//    signum y) is a sign-bit comparison of u, no FP64 work;
+//  * lengths are divided by L = (1.5 h2)^(1/5) per ray, which makes the force constant -1
+//    (one multiply less per force evaluation);
+//  * |pos|^-5 comes from one MUFU.RSQ64H seed and a second-order correction in 7 DP
+//    instructions instead of sqrt, three multiplies and a divide;
+//  * the stage velocities are eliminated algebraically (p3 = p2 + (h/2)^2 a1, ...);
+//  * horizon / escape tests compare the bit patterns of positive doubles as integers.
 #pragma once
 
 #include "bsb_common.cuh"
@@ -62,21 +68,34 @@ BSB_HD double rsqrt_seed(double x)
 #endif
 }
 
-// k * q^(-5/2), relative error ~2 ulp.  With y0 = q^-1/2 (1+d) and e = 1 - q y0^2 = -(2d + d^2):
-//   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + O(e^3)),  |e| <~ 2^-19.
-BSB_HD double rinv5k(double q, double k)
+// q^(-5/2), relative error ~1e-15.  With y0 = q^-1/2 (1+d) from the seed and m = q y0^2 = 1 - e:
+//   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + O(e^3))
+//            = y0^5 (7.875 - 11.25 m + 4.375 m^2),      |e| <~ 2^-19  =>  O(e^3) <~ 5e-17.
+// 7 DP instructions + 1 MUFU.
+BSB_HD double rinv5(double q)
 {
     const double y0 = rsqrt_seed(q);
-    const double t = q * y0;
-    const double e = fma_(-t, y0, 1.0);
-    const double p = fma_(4.375, e, 2.5);
     const double y2 = y0 * y0;
+    const double m = q * y2;
     const double y4 = y2 * y2;
-    const double yk = y0 * k;
-    const double y5k = y4 * yk;
-    const double ep = e * p;
-    return fma_(y5k, ep, y5k);
+    const double y5 = y4 * y0;
+    const double c = fma_(fma_(4.375, m, -11.25), m, 7.875);
+    return y5 * c;
 }
+
+BSB_HD long long dbits(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(x);
+#else
+    union { double d; long long i; } t;
+    t.d = x;
+    return t.i;
+#endif
+}
+
+// -1 / +1 from the sign bit (an exact zero counts as its sign bit says)
+BSB_HD int sign_of(double x) { return (int)(dbits(x) >> 63) | 1; }
 
 // ---- ray generation: src/Raytracer.hs:40-51, bit-exact with the reference's op order ----
 BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
@@ -98,69 +117,104 @@ BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
     }
 }
 
-// State of one ray between step blocks.
+// State of one ray between step blocks.  Coordinates are in the ray's own orbital plane,
+// basis (f1, f2) with f2 HORIZONTAL (so scene-y = f1y * u and a disk-plane crossing is a sign
+// change of u), and divided by L = (1.5 h2)^(1/5) so that the equation of motion is
+// p'' = -p / |p|^5 for every ray (classical RK4 commutes with this linear change of
+// variables, so it is still the reference's discrete map).
 struct RayState {
-    double u, v;       // position in the (e1, e2) plane
-    double du, dv;     // velocity in the plane
-    double q;          // |pos|^2 of the current position
-    double y;          // scene-y of the current position (disk plane is y = 0)
-    double k;          // -1.5 * h2
-    double e2y;        // y component of e2
+    double u, v;       // position / L in the (f1, f2) basis
+    double du, dv;     // velocity / L
+    double q;          // u^2 + v^2
+    double qh, qs;     // horizon and escape thresholds on q: 1/L^2, safe2/L^2
     double acc[4];     // colour accumulated front-to-back (premultiplied RGBA), Raytracer.hs:86
     uint32_t steps;
     int32_t status;    // kAlive / kBlack / kSky / kCapped
+    int32_t side;      // signum class of scene-y at the current position: -1, 0, +1
+    int32_t ysign;     // sign of f1y (scene-y = f1y * u); 0 = the plane is the disk plane
 };
 enum : int32_t { kAlive = 0, kBlack = 1, kSky = 2, kCapped = 3, kIdle = 4 };
 
-// orbital-plane basis for direction `dir`: a = dir.e1, b = |dir - a e1|, e2 = (dir - a e1)/b
-BSB_HD void plane_basis(const FrameParams &P, const double dir[3], double &a, double &b, double e2[3])
+struct RayFrame {
+    double f1[3], f2[3];
+    double L;          // length scale (1.5 h2)^(1/5)
+    double qh;         // 1 / L^2
+    int32_t ysign;
+};
+
+// Orbital-plane frame of the ray through `dir`.  n = cam x dir is the plane normal
+// (|n|^2 = h2, formed exactly as src/Raytracer.hs:73 forms it).
+BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
 {
-    a = dir[0] * P.e1[0] + dir[1] * P.e1[1] + dir[2] * P.e1[2];
-    double w0 = fma_(-a, P.e1[0], dir[0]);
-    double w1 = fma_(-a, P.e1[1], dir[1]);
-    double w2 = fma_(-a, P.e1[2], dir[2]);
-    const double b2 = w0 * w0 + w1 * w1 + w2 * w2;
-    if (b2 < 1e-60) {
-        // radial ray: any unit vector orthogonal to e1 will do (h2 = 0, the motion is a line)
-        const double ax = fabs(P.e1[0]), ay = fabs(P.e1[1]), az = fabs(P.e1[2]);
-        double t0 = 0, t1 = 0, t2 = 0;
-        if (ax <= ay && ax <= az) t0 = 1; else if (ay <= az) t1 = 1; else t2 = 1;
-        const double d = t0 * P.e1[0] + t1 * P.e1[1] + t2 * P.e1[2];
-        w0 = t0 - d * P.e1[0]; w1 = t1 - d * P.e1[1]; w2 = t2 - d * P.e1[2];
-        const double n = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
-        e2[0] = w0 / n; e2[1] = w1 / n; e2[2] = w2 / n;
-        b = 0.0;
+    const double n0 = sub_rn(mul_rn(P.cam[1], dir[2]), mul_rn(P.cam[2], dir[1]));
+    const double n1 = sub_rn(mul_rn(P.cam[2], dir[0]), mul_rn(P.cam[0], dir[2]));
+    const double n2 = sub_rn(mul_rn(P.cam[0], dir[1]), mul_rn(P.cam[1], dir[0]));
+    const double h2 = add_rn(add_rn(mul_rn(n0, n0), mul_rn(n1, n1)), mul_rn(n2, n2));  // :73
+    // p'' = -1.5 h2 p/|p|^5 with p = L p~ gives p~'' = -(1.5 h2 / L^5) p~/|p~|^5: L^5 = 1.5 h2
+    double l5 = 1.5 * h2;
+    if (!(l5 > 1e-280)) l5 = 1e-280;  // radial ray: the force term underflows to zero, as it should
+    F.L = pow(l5, 0.2);
+    const double iL = 1.0 / F.L;
+    F.qh = iL * iL;
+    const double s2 = n0 * n0 + n2 * n2;
+    if (!(h2 > 1e-280) || !(s2 > 1e-28 * h2)) {
+        // radial ray (no plane) or a plane that IS the disk plane: f1 = cam/|cam|, f2 any
+        // in-plane unit vector orthogonal to it.
+        F.f1[0] = P.e1[0]; F.f1[1] = P.e1[1]; F.f1[2] = P.e1[2];
+        double w0, w1, w2;
+        if (h2 > 1e-280) {  // f2 = nhat x f1
+            const double in = 1.0 / sqrt(h2);
+            w0 = (n1 * P.e1[2] - n2 * P.e1[1]) * in;
+            w1 = (n2 * P.e1[0] - n0 * P.e1[2]) * in;
+            w2 = (n0 * P.e1[1] - n1 * P.e1[0]) * in;
+        } else {
+            const double ax = fabs(P.e1[0]), ay = fabs(P.e1[1]), az = fabs(P.e1[2]);
+            double t0 = 0, t1 = 0, t2 = 0;
+            if (ax <= ay && ax <= az) t0 = 1; else if (ay <= az) t1 = 1; else t2 = 1;
+            const double d = t0 * P.e1[0] + t1 * P.e1[1] + t2 * P.e1[2];
+            w0 = t0 - d * P.e1[0]; w1 = t1 - d * P.e1[1]; w2 = t2 - d * P.e1[2];
+        }
+        const double iw = 1.0 / sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+        F.f2[0] = w0 * iw; F.f2[1] = w1 * iw; F.f2[2] = w2 * iw;
+        F.ysign = (h2 > 1e-280) ? 0 : ((P.e1[1] > 0.0) - (P.e1[1] < 0.0));
         return;
     }
-    b = sqrt(b2);
-    const double ib = 1.0 / b;
-    e2[0] = w0 * ib; e2[1] = w1 * ib; e2[2] = w2 * ib;
+    // general case: f2 along the line of nodes (n x yhat), f1 = nhat x f2; then f1y = -s/|n| < 0
+    const double in = 1.0 / sqrt(h2);
+    const double nh0 = n0 * in, nh1 = n1 * in, nh2 = n2 * in;
+    double g0 = -n2, g1 = 0.0, g2 = n0;
+    const double dp = g0 * nh0 + g2 * nh2;                 // re-orthogonalise against nhat
+    g0 -= dp * nh0; g1 -= dp * nh1; g2 -= dp * nh2;
+    const double ig = 1.0 / sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+    g0 *= ig; g1 *= ig; g2 *= ig;
+    F.f2[0] = g0; F.f2[1] = g1; F.f2[2] = g2;
+    F.f1[0] = nh1 * g2 - nh2 * g1;
+    F.f1[1] = nh2 * g0 - nh0 * g2;
+    F.f1[2] = nh0 * g1 - nh1 * g0;
+    F.ysign = -1;
 }
 
 // traceRay's setup (src/Raytracer.hs:69-75): ray, h2 = |pos x vel|^2, acc = 0
 BSB_HD void ray_init(const FrameParams &P, int x, int y, RayState &s)
 {
-    double dir[3], e2[3], a, b;
+    double dir[3];
+    RayFrame F;
     ray_direction(P, x, y, dir);
-    plane_basis(P, dir, a, b, e2);
-    // h2 exactly as the reference forms it (:73 quadrance (pos `cross` vel))
-    const double c0 = sub_rn(mul_rn(P.cam[1], dir[2]), mul_rn(P.cam[2], dir[1]));
-    const double c1 = sub_rn(mul_rn(P.cam[2], dir[0]), mul_rn(P.cam[0], dir[2]));
-    const double c2 = sub_rn(mul_rn(P.cam[0], dir[1]), mul_rn(P.cam[1], dir[0]));
-    const double h2 = add_rn(add_rn(mul_rn(c0, c0), mul_rn(c1, c1)), mul_rn(c2, c2));
-    s.u = P.r0; s.v = 0.0;
-    s.du = a;   s.dv = b;
-    s.q = P.q0;
-    s.y = P.cam[1];
-    s.k = -1.5 * h2;
-    s.e2y = e2[1];
+    ray_frame(P, dir, F);
+    const double iL = 1.0 / F.L;
+    s.u = (P.cam[0] * F.f1[0] + P.cam[1] * F.f1[1] + P.cam[2] * F.f1[2]) * iL;
+    s.v = (P.cam[0] * F.f2[0] + P.cam[1] * F.f2[1] + P.cam[2] * F.f2[2]) * iL;
+    s.du = (dir[0] * F.f1[0] + dir[1] * F.f1[1] + dir[2] * F.f1[2]) * iL;
+    s.dv = (dir[0] * F.f2[0] + dir[1] * F.f2[1] + dir[2] * F.f2[2]) * iL;
+    s.q = P.q0 * F.qh;               // the reference tests quadrance(cam) on the first step
+    s.qh = F.qh;
+    s.qs = P.safe2 * F.qh;
     s.acc[0] = s.acc[1] = s.acc[2] = s.acc[3] = 0.0;
     s.steps = 0;
     s.status = kAlive;
+    s.side = (P.cam[1] > 0.0) - (P.cam[1] < 0.0);  // signum of the exact starting y (:96)
+    s.ysign = F.ysign;
 }
-
-// signum class with Haskell's semantics for zeros: -1, 0, +1 (Raytracer.hs:96 compares signum y' /= signum y)
-BSB_HD int sign_class(double y) { return (y > 0.0) - (y < 0.0); }
 
 // massiv-io HSI -> RGB (see oracle/oracle_thirdparty.c for the statement of the formula)
 BSB_HD void hsi_to_rgb(double hp, double s, double i, double rgb[3])
@@ -215,47 +269,60 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
 // Advance one ray by at most `max_steps` RK4 steps (colorize', src/Raytracer.hs:80-85).
 // The reference takes the step first and then tests the OLD position; testing first and
 // skipping the (unused) last step gives the same result with one step less per ray.
+// 64 DP instructions + 4 MUFU per step; every per-step test is integer-only.
 BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
-    double u = s.u, v = s.v, du = s.du, dv = s.dv, q = s.q, y = s.y;
-    const double k = s.k;
-    const double e1y = P.e1[1], e2y = s.e2y;
-    const bool disk = P.disk_opacity != 0.0;
+    double u = s.u, v = s.v, du = s.du, dv = s.dv, q = s.q;
+    double qs_d = s.qs;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+d"(qs_d));  // keep the threshold in a register (ptxas would re-multiply it every step)
+#endif
+    const long long qh = dbits(s.qh), qs = dbits(qs_d);  // q > 0: doubles order like their bits
+    const int ysign = s.ysign;
+    int side = s.side;
+    const bool disk = P.disk_on != 0;
+    const uint32_t left = P.step_cap > s.steps ? P.step_cap - s.steps : 0u;
+    const uint32_t budget = max_steps < left ? max_steps : left;
     uint32_t n = 0;
     int32_t status = kAlive;
-    while (n < max_steps) {
-        if (q < 1.0) { status = kBlack; break; }                   // :93 passed the horizon
-        if (q > P.safe2) { status = kSky; break; }                 // :94 escaped
-        if (s.steps + n >= P.step_cap) { status = kCapped; break; }
-        // ---- classical RK4 on y' = f(y), f(vel,pos) = (k |pos|^-5 pos, vel)   (:113-134)
-        const double g1 = rinv5k(q, k);
-        const double a1u = g1 * u, a1v = g1 * v;
+    for (;;) {
+        const long long qi = dbits(q);
+        if (qi < qh) { status = kBlack; break; }                   // :93 passed the horizon
+        if (qi > qs) { status = kSky; break; }                     // :94 escaped
+        if (n >= budget) break;
+        // ---- classical RK4 on y' = f(y), f(vel,pos) = (-pos/|pos|^5, vel)   (:113-134)
+        const double g1 = rinv5(q);
+        const double a1u = g1 * u, a1v = g1 * v;                   // a_i hold MINUS the acceleration
         const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
-        const double g2 = rinv5k(fma_(p2u, p2u, p2v * p2v), k);
+        const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v));
         const double a2u = g2 * p2u, a2v = g2 * p2v;
-        const double p3u = fma_(P.hh2, a1u, p2u), p3v = fma_(P.hh2, a1v, p2v);
-        const double g3 = rinv5k(fma_(p3u, p3u, p3v * p3v), k);
+        const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
+        const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v));
         const double a3u = g3 * p3u, a3v = g3 * p3v;
         const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
-        const double p4u = fma_(P.hhh, a2u, peu), p4v = fma_(P.hhh, a2v, pev);
-        const double g4 = rinv5k(fma_(p4u, p4u, p4v * p4v), k);
+        const double p4u = fma_(-P.hhh, a2u, peu), p4v = fma_(-P.hhh, a2v, pev);
+        const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v));
         const double a4u = g4 * p4u, a4v = g4 * p4v;
         const double s23u = a2u + a3u, s23v = a2v + a3v;
-        const double nu = fma_(P.hsq6, a1u + s23u, peu);
-        const double nv = fma_(P.hsq6, a1v + s23v, pev);
-        du = fma_(P.h6, fma_(2.0, s23u, a1u) + a4u, du);
-        dv = fma_(P.h6, fma_(2.0, s23v, a1v) + a4v, dv);
+        const double nu = fma_(-P.hsq6, a1u + s23u, peu);
+        const double nv = fma_(-P.hsq6, a1v + s23v, pev);
+        du = fma_(-P.h6, fma_(2.0, s23u, a1u) + a4u, du);
+        dv = fma_(-P.h6, fma_(2.0, s23v, a1v) + a4v, dv);
         const double nq = fma_(nu, nu, nv * nv);
-        const double ny = fma_(e1y, nu, e2y * nv);
         n++;
-        // ---- disk crossing between the old and the new position (:96-98)
-        if (disk && sign_class(ny) != sign_class(y)) {
-            const double r2ave = (ny * q - y * nq) / (ny - y);      // :102
+        // ---- disk crossing between the old and the new position (:96-98): scene-y = f1y * u
+        const int nside = ysign * sign_of(nu);
+        if (disk && nside != side) {
+            // :102 r2ave = (y' r2 - y r2') / (y' - y); f1y cancels, 1/qh = L^2 restores the scale
+            const double r2ave = ((nu * q - u * nq) / (nu - u)) / s.qh;
             if (r2ave > P.din2 && r2ave < P.dout2) disk_layer(P, r2ave, s.acc);
         }
-        u = nu; v = nv; q = nq; y = ny;
+        side = nside;
+        u = nu; v = nv; q = nq;
     }
-    s.u = u; s.v = v; s.du = du; s.dv = dv; s.q = q; s.y = y;
+    if (status == kAlive && s.steps + n >= P.step_cap) status = kCapped;
+    s.u = u; s.v = v; s.du = du; s.dv = dv; s.q = q;
+    s.side = side;
     s.steps += n;
     s.status = status;
 }
@@ -336,11 +403,13 @@ BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, i
     if (s.status == kSky) {
         double c[4] = { 0, 0, 0, 1.0 };
         if (P.tree.n_stars > 0) {
-            double dir[3], e2[3], a, b;
+            double dir[3];
+            RayFrame F;
             ray_direction(P, x, y, dir);
-            plane_basis(P, dir, a, b, e2);
-            const double vel[3] = { fma_(s.du, P.e1[0], s.dv * e2[0]), fma_(s.du, P.e1[1], s.dv * e2[1]),
-                                    fma_(s.du, P.e1[2], s.dv * e2[2]) };
+            ray_frame(P, dir, F);
+            const double vu = s.du * F.L, vv = s.dv * F.L;   // :94 the pre-step velocity, unscaled
+            const double vel[3] = { fma_(vu, F.f1[0], vv * F.f2[0]), fma_(vu, F.f1[1], vv * F.f2[1]),
+                                    fma_(vu, F.f1[2], vv * F.f2[2]) };
             hits = star_lookup(P, top, n_top, vel, c);
         }
         blend_under(acc, c);

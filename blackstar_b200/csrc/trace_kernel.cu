@@ -75,8 +75,8 @@ __device__ __forceinline__ double quad_mean(double v)
     return __dmul_rn(0.25, __dadd_rn(__dadd_rn(__dadd_rn(v, b), c), d));
 }
 
-template <bool SS>
-__global__ void __launch_bounds__(kTraceThreads, 3)
+template <bool SS, int MINB>
+__global__ void __launch_bounds__(kTraceThreads, MINB)
 trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ out, TraceCounters *ctr)
 {
     __shared__ double s_top[kSmemTreeNodes];
@@ -226,7 +226,7 @@ trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ 
 }
 
 // ---- numerics self-test of the |pos|^-5 kernel primitive: max relative error of
-// rinv5k(q, 1) against pow(q, -2.5) over n log-spaced q in [q_lo, q_hi]
+// rinv5(q) against pow(q, -2.5) over n log-spaced q in [q_lo, q_hi]
 __global__ void rinv5_selftest_kernel(double q_lo, double q_hi, int n, double *max_rel, double *max_seed_err)
 {
     double worst = 0.0, worst_seed = 0.0;
@@ -234,7 +234,7 @@ __global__ void rinv5_selftest_kernel(double q_lo, double q_hi, int n, double *m
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double q = q_lo * exp(lr * ((double)i + 0.5) / (double)n);
         const double ref = pow(q, -2.5);
-        const double got = rinv5k(q, 1.0);
+        const double got = rinv5(q);
         worst = fmax(worst, fabs(got - ref) / ref);
         const double y0 = rsqrt_seed(q);
         worst_seed = fmax(worst_seed, fabs(fma(-q * y0, y0, 1.0)));
@@ -261,7 +261,8 @@ static int persistent_grid(K kernel, int n_sms)
     return n_sms * per_sm;
 }
 
-// variant: 0 = tiles, 1 = refill(block 16, min 8 lanes), 2 = refill(block 8, min 4), 3 = refill(block 32, min 8)
+// variant: 0 = tiles, 1 = refill(block 16, min 8 lanes), 2 = refill(block 8, min 4), 3 = refill(block 32, min 8),
+//          4 = tiles compiled for 4 CTAs/SM (64 registers)
 cudaError_t launch_trace(const FrameParams &P, float4 *out, TraceCounters *ctr, int n_sms, int variant,
                          cudaStream_t stream)
 {
@@ -278,14 +279,16 @@ cudaError_t launch_trace(const FrameParams &P, float4 *out, TraceCounters *ctr, 
         case 1: BSB_LAUNCH((trace_refill_kernel<true, 16, 2>)); break;
         case 2: BSB_LAUNCH((trace_refill_kernel<true, 8, 1>)); break;
         case 3: BSB_LAUNCH((trace_refill_kernel<true, 32, 2>)); break;
-        default: BSB_LAUNCH((trace_tiles_kernel<true>)); break;
+        case 4: BSB_LAUNCH((trace_tiles_kernel<true, 4>)); break;
+        default: BSB_LAUNCH((trace_tiles_kernel<true, 3>)); break;
         }
     } else {
         switch (variant) {
         case 1: BSB_LAUNCH((trace_refill_kernel<false, 16, 8>)); break;
         case 2: BSB_LAUNCH((trace_refill_kernel<false, 8, 4>)); break;
         case 3: BSB_LAUNCH((trace_refill_kernel<false, 32, 8>)); break;
-        default: BSB_LAUNCH((trace_tiles_kernel<false>)); break;
+        case 4: BSB_LAUNCH((trace_tiles_kernel<false, 4>)); break;
+        default: BSB_LAUNCH((trace_tiles_kernel<false, 3>)); break;
         }
     }
 #undef BSB_LAUNCH

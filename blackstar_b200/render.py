@@ -65,8 +65,14 @@ class Renderer:
         self._check(self._L.bsb_set_option(self._ctx, key.encode(), float(value)))
 
     def set_stream(self, cuda_stream: Optional[int]):
-        """Run device 0's work on an existing cudaStream_t (e.g. torch's current stream)."""
-        self._check(self._L.bsb_set_stream(self._ctx, ctypes.c_void_p(cuda_stream or 0)))
+        """Run device 0's work on an existing cudaStream_t (e.g. torch's current stream).
+        ``None`` restores the ctx's own stream; handle 0 (torch's default stream) is passed as
+        cudaStreamLegacy, because NULL means "restore" in the C ABI."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1  # (cudaStream_t)0x1 == cudaStreamLegacy
+        self._check(self._L.bsb_set_stream(self._ctx, ctypes.c_void_p(handle)))
 
     # ------------------------------------------------------------------ star map
     def set_stars(self, stars: Optional[np.ndarray]):

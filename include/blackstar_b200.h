@@ -103,7 +103,7 @@ const char *bsb_last_error(const bsb_ctx *ctx);
 const char *bsb_version(void);
 /* Use an existing cudaStream_t (as void*) for device 0's work instead of the ctx's own
  * stream, so a caller that owns the stream can bracket calls with its own events.
- * NULL restores the ctx's stream. */
+ * NULL restores the ctx's stream; pass cudaStreamLegacy ((void*)1) for the default stream. */
 int bsb_set_stream(bsb_ctx *ctx, void *cuda_stream);
 
 /* Tuning knobs.  "trace_variant": 0 = one tile of 32 rays per warp, 1..3 = persistent warps

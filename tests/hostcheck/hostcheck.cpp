@@ -89,6 +89,6 @@ void hc_star_lookup(void *p, double intensity, double saturation, const double v
     *hits = star_lookup(P, P.tree.split, n_top, vel, rgb);
 }
 
-double hc_rinv5k(double q, double k) { return rinv5k(q, k); }
+double hc_rinv5(double q) { return rinv5(q); }
 
 }  // extern "C"

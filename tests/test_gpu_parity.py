@@ -48,7 +48,7 @@ def rgb(img):
 def test_rinv5_primitive_on_device(rnd):
     rel, seed = rnd.selftest_rinv5(0.25, 1e5, 1 << 20)
     print(f"rinv5k max rel err {rel:.3e}; MUFU.RSQ64H seed residual {seed:.3e} (2^{np.log2(seed):.1f})")
-    assert rel < 2e-15          # ~ a few ulp of double
+    assert rel < 3e-15          # ~ a few ulp of double
     assert seed < 2.0 ** -17    # the correction polynomial is designed for |e| <~ 2^-19
 
 
@@ -79,7 +79,7 @@ def test_scene_vs_oracle_all_schedules(rnd, scenes_dir, stars40k, scene):
     rnd.set_stars(stars40k)
     ref, rsteps = po.render(cfg, po.Tree(stars40k))
     imgs = []
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         rnd.set_option("trace_variant", variant)
         img = rnd.render(cfg)
         assert np.abs(rgb(img) - ref).max() < TOL, f"variant {variant}"
@@ -187,6 +187,30 @@ def test_camera_inside_horizon_and_radial_ray(rnd, scenes_dir):
     img = rnd.render(radial)
     ref, _ = po.render(radial, None)
     assert np.abs(rgb(img) - ref).max() < TOL
+
+
+@pytest.mark.parametrize("case", ["cam_in_disk_plane", "cam_inside_annulus", "cam_on_y_axis", "close_small_step"])
+def test_degenerate_geometry(rnd, scenes_dir, stars40k, case):
+    # orbital planes through the y axis / in the disk plane, exact-zero signum at the start
+    base = config.load_config(f"{scenes_dir}/default.yaml")
+    if case == "cam_in_disk_plane":
+        cfg = config.Config(scene=dataclasses.replace(base.scene, resolution=(65, 65)),
+                            camera=dataclasses.replace(base.camera, position=(0.0, 0.0, -20.0), lookAt=(0.0, 0.0, 0.0), upVec=(0.0, 1.0, 0.0)))
+    elif case == "cam_inside_annulus":
+        cfg = config.Config(scene=dataclasses.replace(base.scene, resolution=(64, 64), diskInner=3.0, diskOuter=30.0),
+                            camera=dataclasses.replace(base.camera, position=(0.0, 0.0, -20.0), lookAt=(0.0, 0.0, 0.0), upVec=(0.0, 1.0, 0.0)))
+    elif case == "cam_on_y_axis":
+        cfg = config.Config(scene=dataclasses.replace(base.scene, resolution=(33, 33)),
+                            camera=dataclasses.replace(base.camera, position=(0.0, 5.0, 0.0), lookAt=(0.0, 0.0, 0.0), upVec=(0.0, 0.0, 1.0)))
+    else:
+        cfg = config.Config(scene=dataclasses.replace(base.scene, resolution=(32, 32), stepSize=0.1),
+                            camera=dataclasses.replace(base.camera, position=(3.0, 0.5, 0.0), lookAt=(0.0, 0.0, 3.0)))
+    rnd.set_stars(stars40k)
+    rnd.set_option("trace_variant", 0)
+    img = rnd.render(cfg)
+    ref, rsteps = po.render(cfg, po.Tree(stars40k))
+    assert np.abs(rgb(img) - ref).max() < TOL
+    assert rnd.last_stats["steps"] == rsteps - img.shape[0] * img.shape[1]
 
 
 def test_full_size_rows_default_1080p(rnd, scenes_dir):
