@@ -94,8 +94,17 @@ BSB_HD long long dbits(double x)
 #endif
 }
 
-// -1 / +1 from the sign bit (an exact zero counts as its sign bit says)
-BSB_HD int sign_of(double x) { return (int)(dbits(x) >> 63) | 1; }
+BSB_HD int hi32(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    return (int)(dbits(x) >> 32);
+#endif
+}
+
+// 0 for a clear sign bit, -1 for a set one
+BSB_HD int sign_code(double x) { return hi32(x) >> 31; }
 
 // ---- ray generation: src/Raytracer.hs:40-51, bit-exact with the reference's op order ----
 BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
@@ -130,9 +139,11 @@ struct RayState {
     double acc[4];     // colour accumulated front-to-back (premultiplied RGBA), Raytracer.hs:86
     uint32_t steps;
     int32_t status;    // kAlive / kBlack / kSky / kCapped
-    int32_t side;      // signum class of scene-y at the current position: -1, 0, +1
-    int32_t ysign;     // sign of f1y (scene-y = f1y * u); 0 = the plane is the disk plane
+    int32_t side;      // sign code (0 / -1) that u has on the current side of the disk plane;
+                       // kSideZero = the reference's signum y is 0 here (any move is a crossing);
+                       // kSideNever = this ray's plane is the disk plane (signum y stays 0)
 };
+enum : int32_t { kSideZero = 1, kSideNever = 2 };
 enum : int32_t { kAlive = 0, kBlack = 1, kSky = 2, kCapped = 3, kIdle = 4 };
 
 struct RayFrame {
@@ -212,8 +223,11 @@ BSB_HD void ray_init(const FrameParams &P, int x, int y, RayState &s)
     s.acc[0] = s.acc[1] = s.acc[2] = s.acc[3] = 0.0;
     s.steps = 0;
     s.status = kAlive;
-    s.side = (P.cam[1] > 0.0) - (P.cam[1] < 0.0);  // signum of the exact starting y (:96)
-    s.ysign = F.ysign;
+    // signum of the exact starting y (:96), expressed as the sign u must have on that side
+    const int sy = (P.cam[1] > 0.0) - (P.cam[1] < 0.0);
+    if (F.ysign == 0) s.side = kSideNever;            // y = 0 along the whole ray: signum never changes
+    else if (sy == 0) s.side = kSideZero;             // signum 0 /= signum y' on the first step
+    else s.side = (sy * F.ysign > 0) ? 0 : -1;
 }
 
 // massiv-io HSI -> RGB (see oracle/oracle_thirdparty.c for the statement of the formula)
@@ -266,63 +280,100 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
     blend_under(acc, c);
 }
 
+// One classical RK4 step of y' = f(y), f(vel,pos) = (-pos/|pos|^5, vel)  (src/Raytracer.hs:113-134)
+// from (u, v, du, dv) with q = u^2 + v^2 to (nu, nv, du, dv) with nq.  64 DP + 4 MUFU.
+BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double &du, double &dv,
+                     double &nu, double &nv, double &nq)
+{
+    const double g1 = rinv5(q);
+    const double a1u = g1 * u, a1v = g1 * v;                   // a_i hold MINUS the acceleration
+    const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
+    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v));
+    const double a2u = g2 * p2u, a2v = g2 * p2v;
+    const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
+    const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v));
+    const double a3u = g3 * p3u, a3v = g3 * p3v;
+    const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
+    const double p4u = fma_(-P.hhh, a2u, peu), p4v = fma_(-P.hhh, a2v, pev);
+    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v));
+    const double a4u = g4 * p4u, a4v = g4 * p4v;
+    const double s23u = a2u + a3u, s23v = a2v + a3v;
+    nu = fma_(-P.hsq6, a1u + s23u, peu);
+    nv = fma_(-P.hsq6, a1v + s23v, pev);
+    du = fma_(-P.h6, fma_(2.0, s23u, a1u) + a4u, du);
+    dv = fma_(-P.h6, fma_(2.0, s23v, a1v) + a4v, dv);
+    nq = fma_(nu, nu, nv * nv);
+}
+
 // Advance one ray by at most `max_steps` RK4 steps (colorize', src/Raytracer.hs:80-85).
 // The reference takes the step first and then tests the OLD position; testing first and
 // skipping the (unused) last step gives the same result with one step less per ray.
-// 64 DP instructions + 4 MUFU per step; every per-step test is integer-only.
+// The fast loop is unrolled twice over two register sets (A -> B -> A) so no state is copied;
+// per step it costs 64 DP + 4 MUFU + ~20 integer/control instructions.  Rare events
+// (termination, disk crossing, a radius whose high word equals a threshold's) leave it and are
+// resolved exactly outside.
 BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
-    double u = s.u, v = s.v, du = s.du, dv = s.dv, q = s.q;
-    double qs_d = s.qs;
-#if defined(__CUDA_ARCH__)
-    asm volatile("" : "+d"(qs_d));  // keep the threshold in a register (ptxas would re-multiply it every step)
-#endif
-    const long long qh = dbits(s.qh), qs = dbits(qs_d);  // q > 0: doubles order like their bits
-    const int ysign = s.ysign;
+    double ua = s.u, va = s.v, qa = s.q, du = s.du, dv = s.dv;
+    double ub = ua, vb = va, qb = qa;
+    // q > 0, so doubles order like their bit patterns.  Fast test on the high words: strictly
+    // between the two thresholds' high words => neither the horizon nor the escape test fires.
+    const long long qh = dbits(s.qh), qs = dbits(s.qs);
+    const int lo_hi = hi32(s.qh) + 1;
+    const unsigned span = (unsigned)(hi32(s.qs) - lo_hi);
     int side = s.side;
-    const bool disk = P.disk_on != 0;
+    const bool disk = P.disk_on != 0 && side != kSideNever;
+    const int dmask = disk ? (int)0x80000000 : 0;              // sign-bit compare enabled?
     const uint32_t left = P.step_cap > s.steps ? P.step_cap - s.steps : 0u;
     const uint32_t budget = max_steps < left ? max_steps : left;
-    uint32_t n = 0;
+    uint32_t remaining = budget;
     int32_t status = kAlive;
+    // `side` as a word whose sign bit is the sign u has on the current side of the disk plane
+    int side_word = (side == -1) ? (int)0x80000000 : 0;
+    bool first_is_zero = disk && side == kSideZero;             // signum y = 0 at the start (:96)
     for (;;) {
-        const long long qi = dbits(q);
-        if (qi < qh) { status = kBlack; break; }                   // :93 passed the horizon
-        if (qi > qs) { status = kSky; break; }                     // :94 escaped
-        if (n >= budget) break;
-        // ---- classical RK4 on y' = f(y), f(vel,pos) = (-pos/|pos|^5, vel)   (:113-134)
-        const double g1 = rinv5(q);
-        const double a1u = g1 * u, a1v = g1 * v;                   // a_i hold MINUS the acceleration
-        const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
-        const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v));
-        const double a2u = g2 * p2u, a2v = g2 * p2v;
-        const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
-        const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v));
-        const double a3u = g3 * p3u, a3v = g3 * p3v;
-        const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
-        const double p4u = fma_(-P.hhh, a2u, peu), p4v = fma_(-P.hhh, a2v, pev);
-        const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v));
-        const double a4u = g4 * p4u, a4v = g4 * p4v;
-        const double s23u = a2u + a3u, s23v = a2v + a3v;
-        const double nu = fma_(-P.hsq6, a1u + s23u, peu);
-        const double nv = fma_(-P.hsq6, a1v + s23v, pev);
-        du = fma_(-P.h6, fma_(2.0, s23u, a1u) + a4u, du);
-        dv = fma_(-P.h6, fma_(2.0, s23v, a1v) + a4v, dv);
-        const double nq = fma_(nu, nu, nv * nv);
-        n++;
-        // ---- disk crossing between the old and the new position (:96-98): scene-y = f1y * u
-        const int nside = ysign * sign_of(nu);
-        if (disk && nside != side) {
-            // :102 r2ave = (y' r2 - y r2') / (y' - y); f1y cancels, 1/qh = L^2 restores the scale
-            const double r2ave = ((nu * q - u * nq) / (nu - u)) / s.qh;
-            if (r2ave > P.din2 && r2ave < P.dout2) disk_layer(P, r2ave, s.acc);
+        // ---- exact tests on the current position (A)
+        {
+            const long long qi = dbits(qa);
+            if (qi < qh) { status = kBlack; break; }               // :93 passed the horizon
+            if (qi > qs) { status = kSky; break; }                 // :94 escaped
         }
-        side = nside;
-        u = nu; v = nv; q = nq;
+        if (remaining == 0) break;
+        // ---- one careful step A -> B, then hand over to the fast loop
+        rk4_step(P, ua, va, qa, du, dv, ub, vb, qb);
+        remaining--;
+        int ev = 0;                                                // 1: crossing A->B, 2: crossing B->A
+        if (first_is_zero || (((hi32(ub) ^ side_word) & dmask) < 0)) ev = 1;
+        first_is_zero = false;
+        if (ev == 0) {
+            for (;;) {
+                // B is current
+                if ((unsigned)(hi32(qb) - lo_hi) >= span || remaining == 0) { ua = ub; va = vb; qa = qb; break; }
+                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa);
+                remaining--;
+                if (((hi32(ua) ^ side_word) & dmask) < 0) { ev = 2; break; }
+                // A is current
+                if ((unsigned)(hi32(qa) - lo_hi) >= span || remaining == 0) break;
+                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb);
+                remaining--;
+                if (((hi32(ub) ^ side_word) & dmask) < 0) { ev = 1; break; }
+            }
+        }
+        if (ev != 0) {
+            // old position o, new position w
+            const double uo = ev == 1 ? ua : ub, qo = ev == 1 ? qa : qb;
+            const double uw = ev == 1 ? ub : ua, vw = ev == 1 ? vb : va, qw = ev == 1 ? qb : qa;
+            // :102 r2ave = (y' r2 - y r2') / (y' - y); f1y cancels, 1/qh = L^2 restores the scale
+            const double r2ave = ((uw * qo - uo * qw) / (uw - uo)) / s.qh;
+            if (r2ave > P.din2 && r2ave < P.dout2) disk_layer(P, r2ave, s.acc);   // :97-98
+            side_word = hi32(uw) & (int)0x80000000;
+            ua = uw; va = vw; qa = qw;
+        }
     }
+    const uint32_t n = budget - remaining;
     if (status == kAlive && s.steps + n >= P.step_cap) status = kCapped;
-    s.u = u; s.v = v; s.du = du; s.dv = dv; s.q = q;
-    s.side = side;
+    s.u = ua; s.v = va; s.du = du; s.dv = dv; s.q = qa;
+    if (disk && n > 0) s.side = side_word < 0 ? -1 : 0;
     s.steps += n;
     s.status = status;
 }
