@@ -200,4 +200,4 @@ def write_img(img: np.ndarray, path: str, renderer: Optional[Renderer] = None):
         if renderer is None:
             raise ValueError("write_img needs a Renderer for the sRGB map of a float image")
         img = renderer.to_srgb8(img)
-    Image.fromarray(img, mode="RGB").save(path, format="PNG")
+    Image.fromarray(np.ascontiguousarray(img)).save(path, format="PNG")

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 echo "== pytest gpu"
 timeout 1500 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -12 | tee gpurun_out/pytest_gpu.txt
-for v in 0 4 1; do
+for v in 0 4; do
   echo "== bench variant $v"
   extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""
   timeout 600 python bench.py --steps 5 --warmup 3 --variant $v $extra > gpurun_out/bench2_v$v.json 2> gpurun_out/bench2_v$v.err
@@ -14,6 +14,6 @@ PY
   tail -3 gpurun_out/bench2_v$v.err
 done
 echo "== ncu full (trace + bloom)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"trace|box3" -s 3 -c 3 -o gpurun_out/prof_r01b \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"trace|box3" -s 3 -c 3 -o gpurun_out/prof_r01c \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_bench2.log 2>&1
 ls -la gpurun_out | tail -8
