@@ -23,11 +23,14 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // One CTA per line of `n` pixels (C = ceil(n / 512) pixels per thread, compile-time).
 //   in  : [lines][n] float4, row-major
 //   out : [n][lines] float4 (transposed)
-//   COMBINE: out = img + strength * blur, img indexed like out.
-template <int C, bool COMBINE>
-__global__ void __launch_bounds__(kBloomThreads, 1)
+//   combine: out = img + strength * blur, img indexed like out.
+// The line lives in registers as float (what the framebuffer holds anyway); every sum is FP64.
+// 48 registers and 3*C*4 KB of shared memory per CTA -> two CTAs per SM up to n = 4096, so one
+// CTA's loads/stores overlap the other's scans.
+template <int C>
+__global__ void __launch_bounds__(kBloomThreads, (C <= 8) ? 2 : 1)
 box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, const float4 *__restrict__ img,
-                      int n, int lines, int r, double norm, double strength)
+                      int n, int lines, int r, double norm, double strength, int combine)
 {
     extern __shared__ double s_mem[];
     constexpr int T = kBloomThreads;
@@ -36,39 +39,34 @@ box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, c
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int line = blockIdx.x;
 
-    double v[C][3];
+    float v[C][3];
 #pragma unroll
     for (int j = 0; j < C; j++) {
         const int x = t * C + j;
         if (x < n) {
             const float4 p = __ldg(&in[(size_t)line * n + x]);
-            v[j][0] = (double)p.x; v[j][1] = (double)p.y; v[j][2] = (double)p.z;
+            v[j][0] = p.x; v[j][1] = p.y; v[j][2] = p.z;
         } else {
-            v[j][0] = v[j][1] = v[j][2] = 0.0;
+            v[j][0] = v[j][1] = v[j][2] = 0.0f;
         }
     }
 
 #pragma unroll 1
     for (int pass = 0; pass < 3; pass++) {
-        // thread-local inclusive sums
-        double run[C][3];
+        // block-wide exclusive offset of this thread's chunk, per channel
+        double excl[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            double a = 0.0;
+            double tot = 0.0;
 #pragma unroll
-            for (int j = 0; j < C; j++) { a += v[j][c]; run[j][c] = a; }
-        }
-        // block-wide exclusive offset of this thread's chunk
-        double incl[3], excl[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            double x = run[C - 1][c];
+            for (int j = 0; j < C; j++) tot += (double)v[j][c];
+            double x = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const double y = __shfl_up_sync(kFullMask, x, o);
                 if (lane >= o) x += y;
             }
-            incl[c] = x;
+            excl[c] = x - tot;                       // exclusive within the warp
             if (lane == 31) s_wt[c * 16 + warp] = x;
         }
         __syncthreads();
@@ -87,13 +85,13 @@ box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, c
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double before_warp = warp > 0 ? s_wt[c * 16 + warp - 1] : 0.0;
-            excl[c] = before_warp + (incl[c] - run[C - 1][c]);
+            double a = excl[c] + (warp > 0 ? s_wt[c * 16 + warp - 1] : 0.0);
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                a += (double)v[j][c];
+                P[c * C * T + j * T + t] = a;
+            }
         }
-#pragma unroll
-        for (int j = 0; j < C; j++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) P[c * C * T + j * T + t] = excl[c] + run[j][c];
         __syncthreads();
         // window [x-r+1, x+r] clipped to the line; everything outside reads as zero (:41-46)
 #pragma unroll
@@ -108,7 +106,7 @@ box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, c
             for (int c = 0; c < 3; c++) {
                 const double a = P[c * C * T + hi_i];
                 const double b = lo >= 0 ? P[c * C * T + lo_i] : 0.0;
-                v[j][c] = x < n ? norm * (a - b) : 0.0;
+                v[j][c] = x < n ? (float)(norm * (a - b)) : 0.0f;
             }
         }
         __syncthreads();
@@ -119,27 +117,28 @@ box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, c
         const int x = t * C + j;
         if (x < n) {
             const size_t o = (size_t)x * lines + line;
-            if (COMBINE) {
+            if (combine) {
                 const float4 p = __ldg(&img[o]);
-                out[o] = make_float4((float)((double)p.x + strength * v[j][0]), (float)((double)p.y + strength * v[j][1]),
-                                     (float)((double)p.z + strength * v[j][2]), p.w);
+                out[o] = make_float4((float)((double)p.x + strength * (double)v[j][0]),
+                                     (float)((double)p.y + strength * (double)v[j][1]),
+                                     (float)((double)p.z + strength * (double)v[j][2]), p.w);
             } else {
-                out[o] = make_float4((float)v[j][0], (float)v[j][1], (float)v[j][2], 1.0f);
+                out[o] = make_float4(v[j][0], v[j][1], v[j][2], 1.0f);
             }
         }
     }
 }
 
-template <int C, bool COMBINE>
+template <int C>
 static cudaError_t launch_box3_c(const float4 *in, float4 *out, const float4 *img, int n, int lines, int r,
-                                 double strength, cudaStream_t stream)
+                                 double strength, bool combine, cudaStream_t stream)
 {
     const size_t smem = (size_t)(3 * C * kBloomThreads + 3 * 16) * sizeof(double);
-    auto kern = box3_transpose_kernel<C, COMBINE>;
+    auto kern = box3_transpose_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const double norm = 1.0 / (2.0 * (double)r + 1.0);  // src/ImageFilters.hs:51
-    kern<<<lines, kBloomThreads, smem, stream>>>(in, out, img, n, lines, r, norm, strength);
+    kern<<<lines, kBloomThreads, smem, stream>>>(in, out, img, n, lines, r, norm, strength, combine ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -150,9 +149,7 @@ cudaError_t launch_box3_transpose(const float4 *in, float4 *out, const float4 *i
                                   double strength, bool combine, cudaStream_t stream)
 {
     const int c = (n + kBloomThreads - 1) / kBloomThreads;
-#define BSB_BOX(CC)                                                                                   \
-    return combine ? launch_box3_c<CC, true>(in, out, img, n, lines, r, strength, stream)             \
-                   : launch_box3_c<CC, false>(in, out, img, n, lines, r, strength, stream)
+#define BSB_BOX(CC) return launch_box3_c<CC>(in, out, img, n, lines, r, strength, combine, stream)
     if (c <= 1) { BSB_BOX(1); }
     if (c <= 2) { BSB_BOX(2); }
     if (c <= 4) { BSB_BOX(4); }

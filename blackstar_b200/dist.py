@@ -12,7 +12,7 @@ is in libblackstar_b200.so.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -23,6 +23,26 @@ from .config import Config
 def row_tiles(height: int, world: int) -> List[Tuple[int, int]]:
     """Rows [H k/N, H (k+1)/N) for k = 0..N-1 (the same split bsb_render_full uses)."""
     return [(height * k // world, height * (k + 1) // world) for k in range(world)]
+
+
+def balanced_tiles(height: int, rows_per_ms: Sequence[float], extra_ms: Sequence[float]) -> List[Tuple[int, int]]:
+    """Contiguous row tiles such that every rank finishes at the same time.
+
+    Rank k traces ``rows_per_ms[k]`` rows per millisecond (measured on its previous tile) and
+    has ``extra_ms[k]`` of work that only it does (rank 0: receiving the gather + bloom).
+    Solve r_k / rate_k + extra_k = tau with sum r_k = H.  Every rank evaluates this on the same
+    all-gathered numbers, so they agree without further communication.
+    """
+    n = len(rows_per_ms)
+    rate = [max(float(x), 1e-9) for x in rows_per_ms]
+    tau = (height + sum(r * e for r, e in zip(rate, extra_ms))) / sum(rate)
+    want = [max(0.0, r * (tau - e)) for r, e in zip(rate, extra_ms)]
+    scale = height / max(sum(want), 1e-9)
+    edges, acc = [0], 0.0
+    for k in range(n):
+        acc += want[k] * scale
+        edges.append(height if k == n - 1 else min(height, max(edges[-1], int(round(acc)))))
+    return [(edges[k], edges[k + 1]) for k in range(n)]
 
 
 def gather_tiles(full: Optional[torch.Tensor], tile: Optional[torch.Tensor], tiles: List[Tuple[int, int]],
@@ -59,13 +79,48 @@ class TiledFrame:
         self.r, self.cfg, self.rank, self.world, self.device = renderer, cfg, rank, world, device
         W, H = cfg.scene.resolution
         self.W, self.H = W, H
-        self.tiles = row_tiles(H, world)
-        r0, r1 = self.tiles[rank]
         self.full = torch.empty((H, W, 4), dtype=torch.float32, device=device) if rank == 0 else None
-        self.tile = self.full[r0:r1] if rank == 0 else torch.empty((r1 - r0, W, 4), dtype=torch.float32, device=device)
         self.launches = 0
+        self._set_tiles(row_tiles(H, world))
         # run the library's kernels on torch's current stream so they order with the NCCL ops
         self.r.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def _set_tiles(self, tiles: List[Tuple[int, int]]):
+        self.tiles = tiles
+        r0, r1 = tiles[self.rank]
+        if self.rank == 0:
+            self.tile = self.full[r0:r1]
+        else:
+            self.tile = torch.empty((max(r1 - r0, 0), self.W, 4), dtype=torch.float32, device=self.device)
+
+    def calibrate(self, iterations: int = 2):
+        """Adaptive row tiling: measure every rank's trace rate on its current tile and rank 0's
+        rank-only work (gather + bloom), then re-cut the rows so all ranks finish together
+        (``balanced_tiles``).  A renderer in production would do this from frame to frame."""
+        if self.world == 1:
+            return
+        scn = self.cfg.scene
+        for _ in range(iterations):
+            r0, r1 = self.tiles[self.rank]
+            st = self.r.render_device(self.cfg, self.tile.data_ptr(), r0, r1, want_stats=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gather_tiles(self.full, self.tile, self.tiles, self.rank, self.world)
+            if self.rank == 0 and scn.bloomStrength != 0:
+                self.r.bloom_device(scn.bloomStrength, scn.bloomDivider, self.W, self.H, self.full.data_ptr(),
+                                    self.full.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            mine = torch.tensor([float(r1 - r0), float(st["trace_ms"]), e0.elapsed_time(e1) if self.rank == 0 else 0.0],
+                                dtype=torch.float64, device=self.device)
+            allv = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(allv, mine)
+            vals = [v.tolist() for v in allv]
+            rates = [v[0] / max(v[1], 1e-6) for v in vals]
+            extra = [vals[0][2]] + [0.0] * (self.world - 1)
+            self._set_tiles(balanced_tiles(self.H, rates, extra))
 
     def step(self, want_stats: bool = False):
         r0, r1 = self.tiles[self.rank]

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from blackstar_b200 import config
-from blackstar_b200.dist import gather_tiles, row_tiles
+from blackstar_b200.dist import balanced_tiles, gather_tiles, row_tiles
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -23,6 +23,23 @@ def test_row_tiles_partition():
             assert t[0][0] == 0 and t[-1][1] == H
             assert all(a[1] == b[0] for a, b in zip(t, t[1:]))
             assert max(r1 - r0 for r0, r1 in t) - min(r1 - r0 for r0, r1 in t) <= 1
+
+
+def test_balanced_tiles():
+    # equal rates, no extra work -> the plain split
+    assert balanced_tiles(4096, [10.0] * 8, [0.0] * 8) == row_tiles(4096, 8)
+    # rank 0 has 1 ms of rank-only work at 64 rows/ms -> it gets ~56 rows fewer than the others
+    t = balanced_tiles(4096, [64.0] * 8, [1.0] + [0.0] * 7)
+    sizes = [b - a for a, b in t]
+    assert t[0][0] == 0 and t[-1][1] == 4096 and all(a[1] == b[0] for a, b in zip(t, t[1:]))
+    assert sizes[0] == 456 and set(sizes[1:]) == {520}
+    fin = [sz / 64.0 + (1.0 if k == 0 else 0.0) for k, sz in enumerate(sizes)]
+    assert max(fin) - min(fin) < 0.02
+    # a slow rank gets fewer rows; degenerate inputs stay valid partitions
+    t = balanced_tiles(1000, [1.0, 3.0], [0.0, 0.0])
+    assert t == [(0, 250), (250, 1000)]
+    t = balanced_tiles(7, [1.0, 1.0, 1.0], [100.0, 0.0, 0.0])
+    assert t[0] == (0, 0) and t[-1][1] == 7
 
 
 def _free_port():
