@@ -135,6 +135,45 @@ class TiledFrame:
         return st
 
     def step_to_host(self, host_out: Optional[torch.Tensor]):
+        """``step()`` + device->host copy of the finished frame into pinned ``host_out`` (rank 0).
+        Synchronous with respect to the stream: the next frame starts after the copy."""
         self.step()
         if self.rank == 0:
             host_out.copy_(self.full, non_blocking=True)
+
+    # ---- pipelined variant: the copy of frame i overlaps the trace of frame i+1 ------------
+    def enable_double_buffering(self):
+        """Second device frame + a copy stream, so ``step_to_host_pipelined`` can overlap the
+        D2H of one frame with the tracing of the next (what a batch / animation driver does)."""
+        if self.rank != 0 or getattr(self, "_frames", None) is not None:
+            return
+        self._frames = [self.full, torch.empty_like(self.full)]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._copied = [None, None]   # event: the copy out of frame buffer b has finished
+        self._flip = 0
+
+    def step_to_host_pipelined(self, host_outs: Optional[Sequence[torch.Tensor]]):
+        """Like ``step_to_host`` but frame i is rendered into device buffer i % 2 and copied to
+        ``host_outs[i % 2]`` on a side stream.  Call ``drain()`` before reading the last frame."""
+        if self.rank == 0:
+            b = self._flip
+            self._flip ^= 1
+            if self._copied[b] is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._copied[b])  # buffer b is free again
+            self.full = self._frames[b]
+            r0, r1 = self.tiles[0]
+            self.tile = self.full[r0:r1]
+        self.step()
+        if self.rank == 0:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(done)
+                host_outs[b].copy_(self.full, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._copied[b] = ev
+
+    def drain(self):
+        if self.rank == 0 and getattr(self, "_copy_stream", None) is not None:
+            self._copy_stream.synchronize()
