@@ -637,10 +637,10 @@ extern "C" int bsb_measure_fp64_peak(bsb_ctx *ctx, double *tflops)
     if (!ctx || !tflops) return BSB_ERR_INVALID;
     DeviceState &d = ctx->devs[0];
     BSB_CUDA(ctx, cudaSetDevice(d.dev));
-    const int blocks = d.n_sms * 8, iters = 4096;
-    BSB_CUDA(ctx, launch_dfma_peak(d.d_misc, blocks, 256, d.stream));  // warm-up
+    const int blocks = d.n_sms * 8, iters = 8192;
+    BSB_CUDA(ctx, launch_dfma_peak(d.d_misc, blocks, iters, d.stream));  // warm-up at full length: clocks ramp from idle
     double best = 0;
-    for (int rep = 0; rep < 3; rep++) {
+    for (int rep = 0; rep < 5; rep++) {
         BSB_CUDA(ctx, cudaEventRecord(d.ev[0], d.stream));
         BSB_CUDA(ctx, launch_dfma_peak(d.d_misc, blocks, iters, d.stream));
         BSB_CUDA(ctx, cudaEventRecord(d.ev[1], d.stream));
