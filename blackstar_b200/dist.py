@@ -67,6 +67,19 @@ def gather_tiles(full: Optional[torch.Tensor], tile: Optional[torch.Tensor], til
             req.wait()
 
 
+def tiles_from_measurements(height: int, vals: Sequence[Sequence[float]]) -> List[Tuple[int, int]]:
+    """vals[k] = (rows traced, trace ms, rank-only ms) as all-gathered in ``calibrate``.
+    Ranks with too small a tile to time use the mean rate of the others; rank 0's rank-only
+    work is capped at half of an even share so that a hiccup cannot starve it of rows."""
+    n = len(vals)
+    ok = [v[0] / v[1] for v in vals if v[0] >= 8 and v[1] > 1e-3]
+    mean_rate = sum(ok) / len(ok) if ok else 1.0
+    rates = [(v[0] / v[1]) if (v[0] >= 8 and v[1] > 1e-3) else mean_rate for v in vals]
+    even_ms = height / max(sum(rates), 1e-9)
+    extra = [min(max(vals[0][2], 0.0), 0.5 * even_ms)] + [0.0] * (n - 1)
+    return balanced_tiles(height, rates, extra)
+
+
 class TiledFrame:
     """Per-rank state for rendering one scene across the ranks of a process group.
 
@@ -100,6 +113,8 @@ class TiledFrame:
         if self.world == 1:
             return
         scn = self.cfg.scene
+        self.step()                      # untimed: NCCL sets its peer connections up on first use
+        torch.cuda.synchronize()
         for _ in range(iterations):
             r0, r1 = self.tiles[self.rank]
             st = self.r.render_device(self.cfg, self.tile.data_ptr(), r0, r1, want_stats=True)
@@ -118,9 +133,7 @@ class TiledFrame:
             allv = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(allv, mine)
             vals = [v.tolist() for v in allv]
-            rates = [v[0] / max(v[1], 1e-6) for v in vals]
-            extra = [vals[0][2]] + [0.0] * (self.world - 1)
-            self._set_tiles(balanced_tiles(self.H, rates, extra))
+            self._set_tiles(tiles_from_measurements(self.H, vals))
 
     def step(self, want_stats: bool = False):
         r0, r1 = self.tiles[self.rank]

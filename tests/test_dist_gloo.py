@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from blackstar_b200 import config
-from blackstar_b200.dist import balanced_tiles, gather_tiles, row_tiles
+from blackstar_b200.dist import balanced_tiles, gather_tiles, row_tiles, tiles_from_measurements
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -40,6 +40,18 @@ def test_balanced_tiles():
     assert t == [(0, 250), (250, 1000)]
     t = balanced_tiles(7, [1.0, 1.0, 1.0], [100.0, 0.0, 0.0])
     assert t[0] == (0, 0) and t[-1][1] == 7
+
+
+def test_tiles_from_measurements_is_robust():
+    even = [[512, 8.1, 0.0]] * 8
+    assert tiles_from_measurements(4096, even) == row_tiles(4096, 8)
+    t = tiles_from_measurements(4096, [[512, 8.1, 1.2]] + [[512, 8.1, 0.0]] * 7)
+    assert t[0] == (0, 446) and t[-1][1] == 4096
+    # a rank whose tile was too small to time uses the others' rate; a wild rank-only time is capped
+    t = tiles_from_measurements(4096, [[0, 0.0, 30.0]] + [[585, 9.3, 0.0]] * 7)
+    assert 250 < t[0][1] < 330
+    t = tiles_from_measurements(4096, [[512, 8.1, 1e9]] + [[512, 8.3, 0.0]] * 7)
+    assert t[0][1] > 250 and all(b > a for a, b in t)
 
 
 def _free_port():
