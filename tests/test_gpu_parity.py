@@ -246,3 +246,39 @@ def test_full_size_rows_default_aa_4096(rnd, scenes_dir):
     # bloom is linear with non-negative weights: out >= img, and DC gain <= strength*(2r/(2r+1))^6
     pre = rnd.render(cfg, 2046, 2050)
     assert (rgb(full[2046:2050]) >= rgb(pre) - 1e-6).all()
+
+
+def test_full_size_rows_lensing_disk_8192(rnd, scenes_dir):
+    # BASELINE config 4: lensing-disk.yaml at 8192x8192 (x4 supersampling): bands of rows vs the oracle,
+    # and the bloom of an 8192-wide frame (the 16-pixels-per-thread variant of the bloom kernel)
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/lensing-disk.yaml"), 8192, 8192)
+    stars = starmap.synthetic_stars()
+    rnd.set_stars(stars)
+    rnd.set_option("trace_variant", 4)
+    tree = po.Tree(stars)
+    for r0 in (4095, 6000):
+        band = rnd.render(cfg, r0, r0 + 1)
+        ref, _ = po.render(cfg, tree, r0, r0 + 1)
+        assert np.abs(rgb(band) - ref).max() < TOL
+    # bloom at this width: r = 8192 // 25 = 327; compare a 8192 x 40 strip against the oracle
+    rng = np.random.default_rng(11)
+    img = np.ones((40, 8192, 4), dtype=np.float32)
+    img[..., :3] = rng.uniform(0, 1, (40, 8192, 3)).astype(np.float32)
+    got = rnd.bloom(0.15, 25, img)
+    ref = po.bloom(0.15, 25, rgb(img))
+    assert np.abs(rgb(got) - ref).max() < 1e-5
+
+
+def test_animation_frame_1080p_supersampled(rnd, scenes_dir):
+    # BASELINE config 5: a frame of animations/default-ani.yaml (1920x1080, supersampling, bloom 0.7)
+    from blackstar_b200 import animation
+    a = animation.load_animation(os.path.join(os.path.dirname(scenes_dir), "animations", "default-ani.yaml"))
+    cfg = animation.generate_frames(a)[200]
+    stars = starmap.synthetic_stars(100000, seed=6)
+    rnd.set_stars(stars)
+    img = rnd.render(cfg)
+    assert img.shape == (1080, 1920, 4)
+    ref, _ = po.render(cfg, po.Tree(stars), 500, 503)
+    assert np.abs(rgb(img[500:503]) - ref).max() < TOL
+    full = rnd.do_render(cfg)
+    assert np.isfinite(full).all() and (rgb(full) >= rgb(img) - 1e-6).all()
