@@ -24,6 +24,7 @@
 namespace bsb {
 cudaError_t launch_trace(const FrameParams &P, float4 *out, TraceCounters *ctr, int n_sms, int variant,
                          cudaStream_t stream);
+cudaError_t launch_ray_tables(const FrameParams &P, double *vx, double *vy, cudaStream_t stream);
 cudaError_t launch_rinv5_selftest(double q_lo, double q_hi, int n, double *d_out2, cudaStream_t stream);
 cudaError_t launch_box3_transpose(const float4 *in, float4 *out, const float4 *img, int n, int lines, int r,
                                   double strength, bool combine, cudaStream_t stream);
@@ -93,6 +94,8 @@ struct DeviceState {
     float4 *d_tmp = nullptr;   size_t tmp_cap = 0;    // bloom's transposed intermediate
     float4 *d_aux = nullptr;   size_t aux_cap = 0;    // staging for host-buffer bloom / srgb
     uint8_t *d_u8 = nullptr;   size_t u8_cap = 0;
+    double *d_vx = nullptr;    size_t vx_cap = 0;     // per-frame ray tables
+    double *d_vy = nullptr;    size_t vy_cap = 0;
     double *d_misc = nullptr;                         // 2 doubles for self-tests
     cudaEvent_t ev[6] = {};
 };
@@ -161,8 +164,17 @@ int trace_async(bsb_ctx *ctx, DeviceState &d, const bsb_camera *cam, const bsb_s
     P.tree.depth = d.depth;
     P.tree.n_stars = d.n_stars;
     BSB_CUDA(ctx, cudaSetDevice(d.dev));
+    int rc = ensure(ctx, d.d_vx, d.vx_cap, (size_t)P.W2);
+    if (rc) return rc;
+    rc = ensure(ctx, d.d_vy, d.vy_cap, (size_t)P.H2);
+    if (rc) return rc;
     BSB_CUDA(ctx, cudaMemsetAsync(d.d_ctr, 0, sizeof(TraceCounters), d.stream));
     if (ev_begin) BSB_CUDA(ctx, cudaEventRecord(ev_begin, d.stream));
+    if (row1 > row0) {
+        BSB_CUDA(ctx, launch_ray_tables(P, d.d_vx, d.d_vy, d.stream));
+        P.vx_tab = d.d_vx;
+        P.vy_tab = d.d_vy;
+    }
     BSB_CUDA(ctx, launch_trace(P, dst, d.d_ctr, d.n_sms, ctx->trace_variant, d.stream));
     if (ev_end) BSB_CUDA(ctx, cudaEventRecord(ev_end, d.stream));
     BSB_CUDA(ctx, cudaMemcpyAsync(d.h_ctr, d.d_ctr, sizeof(TraceCounters), cudaMemcpyDeviceToHost, d.stream));
@@ -309,6 +321,8 @@ extern "C" void bsb_destroy(bsb_ctx *ctx)
         if (d.d_tmp) cudaFree(d.d_tmp);
         if (d.d_aux) cudaFree(d.d_aux);
         if (d.d_u8) cudaFree(d.d_u8);
+        if (d.d_vx) cudaFree(d.d_vx);
+        if (d.d_vy) cudaFree(d.d_vy);
         if (d.d_misc) cudaFree(d.d_misc);
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
@@ -394,7 +408,7 @@ extern "C" int bsb_render_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_
         stats->rays = rays_of(scn, row1 - row0);
         fill_counter_stats(d, stats);
         stats->n_gpus = 1;
-        stats->launches = row1 > row0 ? 1 : 0;
+        stats->launches = row1 > row0 ? 2 : 0;
         stats->total_ms = ms_since(t0);
         if (stats->capped) return fail(ctx, BSB_ERR_STEPCAP, "a ray reached the step cap (the reference would not terminate)");
     }
@@ -430,7 +444,7 @@ extern "C" int bsb_render(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *
     st.rays = rays_of(scn, row1 - row0);
     fill_counter_stats(d, &st);
     st.n_gpus = 1;
-    st.launches = npix ? 1 : 0;
+    st.launches = npix ? 2 : 0;
     st.total_ms = ms_since(t0);
     if (stats) *stats = st;
     if (st.capped) return fail(ctx, BSB_ERR_STEPCAP, "a ray reached the step cap (the reference would not terminate)");
@@ -526,7 +540,7 @@ int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn
         rc = trace_async(ctx, d, cam, scn, r0[k], r1[k], dst, d.ev[0], d.ev[1]);
         if (rc) return rc;
     }
-    int launches = n;
+    int launches = 2 * n;  // ray tables + trace on every GPU
     // the single collective of the path: gather the tiles on GPU 0 (grouped send/recv)
     if (n > 1) {
         int nrc = ctx->nccl.GroupStart();

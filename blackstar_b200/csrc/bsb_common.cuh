@@ -14,15 +14,21 @@
 
 namespace bsb {
 
-// Star record in device memory: bsb_star (include/blackstar_b200.h) permuted into
-// k-d leaf order.  48 bytes, 16-byte aligned.
+// Star record in device memory, in k-d leaf order (64 bytes, 16-byte aligned).  Besides the
+// position and magnitude of bsb_star it carries the star's colour as three per-channel
+// coefficients: massiv-io's HSI->RGB is linear in the saturation for a fixed hue,
+//   channel = I * (1 + S * k_c),   k_c in {K, -1, 1-K} permuted by the hue sector,
+//   K = cos(a)/cos(b) of the sector (oracle/oracle_thirdparty.c),
+// so the two cosines and the division are paid once per star at upload, not once per hit.
+// kr/kg/kb hold  sat_star * k_c ; the frame's starSaturation multiplies them in the kernel.
 struct StarRec {
     double x, y, z;
-    double hue, sat;
+    double kr, kg, kb;
     int32_t mag;
-    int32_t pad;
+    int32_t pad0;
+    double pad1;
 };
-static_assert(sizeof(StarRec) == 48, "StarRec must mirror bsb_star");
+static_assert(sizeof(StarRec) == 64, "StarRec is 64 bytes");
 
 // Bucketed k-d tree over the unit-sphere star positions (DESIGN.md "star map").
 //   internal nodes: implicit complete binary tree in heap order, n_internal = 2^depth - 1;
@@ -67,6 +73,10 @@ struct FrameParams {
     // sky: src/StarMap.hs:93-115
     double star_intensity, star_saturation;
     StarTreeDev tree;
+    // per-column / per-row ray offsets vx[x], vy[y] (src/Raytracer.hs:49-50), filled by
+    // ray_tables_kernel once per frame; nullptr = compute them per ray
+    const double *vx_tab;
+    const double *vy_tab;
     // grid
     int32_t W2, H2;           // traced grid (doubled under supersampling)
     int32_t W, H;             // final image

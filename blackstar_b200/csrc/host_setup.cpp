@@ -33,6 +33,24 @@ inline V3 normalize(V3 v)
 
 void host_hsi_to_rgb(double h, double s, double i, double rgb[3]) { hsi_to_rgb(h, s, i, rgb); }
 
+// HSI -> RGB as channel = I * (1 + S * k_c) (massiv-io's formula, linear in S for a fixed hue)
+void hue_coefficients(double hp, double k[3])
+{
+    const double pi = 3.141592653589793;
+    const double h = hp * 2 * pi;
+    if (h < 0 || !(h < 2 * pi)) { k[0] = k[1] = k[2] = NAN; return; }  // massiv-io: `error`
+    if (h < 2 * pi / 3) {
+        const double K = std::cos(h) / std::cos(pi / 3 - h);
+        k[0] = K; k[2] = -1.0; k[1] = 1.0 - K;
+    } else if (h < 4 * pi / 3) {
+        const double K = std::cos(h - 2 * pi / 3) / std::cos(h + pi);
+        k[1] = K; k[0] = -1.0; k[2] = 1.0 - K;
+    } else {
+        const double K = std::cos(h - 4 * pi / 3) / std::cos(2 * pi - pi / 3 - h);
+        k[2] = K; k[1] = -1.0; k[0] = 1.0 - K;
+    }
+}
+
 std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int row0, int row1, FrameParams &P)
 {
     if (scn.width <= 0 || scn.height <= 0) return "resolution must be positive";
@@ -170,7 +188,9 @@ void build_star_tree(const bsb_star *stars, size_t n, int leaf_size, HostStarTre
     out.stars.resize(n);
     for (size_t k = 0; k < n; k++) {
         const bsb_star &s = stars[b.idx[k]];
-        out.stars[k] = StarRec{ s.pos[0], s.pos[1], s.pos[2], s.hue, s.sat, s.mag, 0 };
+        double k3[3];
+        hue_coefficients(s.hue, k3);
+        out.stars[k] = StarRec{ s.pos[0], s.pos[1], s.pos[2], s.sat * k3[0], s.sat * k3[1], s.sat * k3[2], s.mag, 0, 0.0 };
     }
 }
 

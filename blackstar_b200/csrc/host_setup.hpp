@@ -32,5 +32,6 @@ bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std
 
 // massiv-io HSI -> RGB on the host (disk colour, once per frame; src/Raytracer.hs:65)
 void host_hsi_to_rgb(double h, double s, double i, double rgb[3]);
+void hue_coefficients(double hue, double k[3]);
 
 }  // namespace bsb

@@ -107,11 +107,20 @@ BSB_HD int hi32(double x)
 BSB_HD int sign_code(double x) { return hi32(x) >> 31; }
 
 // ---- ray generation: src/Raytracer.hs:40-51, bit-exact with the reference's op order ----
-BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
+BSB_HD double pixel_vx(const FrameParams &P, int x)   // :49  fov * (x/w - 0.5)
+{
+    return mul_rn(P.fov, sub_rn(div_rn((double)x, (double)P.W2), 0.5));
+}
+BSB_HD double pixel_vy(const FrameParams &P, int y)   // :50  ((fov * (0.5 - y/h)) * h) / w
 {
     const double w = (double)P.W2, h = (double)P.H2;
-    const double vx = mul_rn(P.fov, sub_rn(div_rn((double)x, w), 0.5));                 // :49
-    const double vy = div_rn(mul_rn(mul_rn(P.fov, sub_rn(0.5, div_rn((double)y, h))), h), w); // :50
+    return div_rn(mul_rn(mul_rn(P.fov, sub_rn(0.5, div_rn((double)y, h))), h), w);
+}
+
+BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
+{
+    const double vx = P.vx_tab ? P.vx_tab[x] : pixel_vx(P, x);
+    const double vy = P.vy_tab ? P.vy_tab[y] : pixel_vy(P, y);
     double u[3];
 #pragma unroll
     for (int k = 0; k < 3; k++)  // :48  (xa_i*vx + ya_i*vy) + (-za_i)*(-1)
@@ -124,6 +133,24 @@ BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
         const double s = sqrt_rn(l);
         dir[0] = div_rn(u[0], s); dir[1] = div_rn(u[1], s); dir[2] = div_rn(u[2], s);
     }
+}
+
+// a^(-1/5) to ~2 ulp: single-precision seed, three Newton steps y <- y (1.2 - 0.2 a y^5)
+// (no division; error 3 d^2 per step).  Replaces pow(a, 0.2) in the per-ray set-up.
+BSB_HD double inv_fifth_root(double a)
+{
+#if defined(__CUDA_ARCH__)
+    double y = (double)exp2f(-0.2f * __log2f((float)a));
+#else
+    double y = (double)std::pow((float)a, -0.2f);
+#endif
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        const double y2 = y * y;
+        const double y5 = (y2 * y2) * y;
+        y = y * fma_(-0.2 * a, y5, 1.2);
+    }
+    return y;
 }
 
 // State of one ray between step blocks.  Coordinates are in the ray's own orbital plane,
@@ -149,6 +176,7 @@ enum : int32_t { kAlive = 0, kBlack = 1, kSky = 2, kCapped = 3, kIdle = 4 };
 struct RayFrame {
     double f1[3], f2[3];
     double L;          // length scale (1.5 h2)^(1/5)
+    double iL;         // 1 / L
     double qh;         // 1 / L^2
     int32_t ysign;
 };
@@ -163,10 +191,12 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
     const double h2 = add_rn(add_rn(mul_rn(n0, n0), mul_rn(n1, n1)), mul_rn(n2, n2));  // :73
     // p'' = -1.5 h2 p/|p|^5 with p = L p~ gives p~'' = -(1.5 h2 / L^5) p~/|p~|^5: L^5 = 1.5 h2
     double l5 = 1.5 * h2;
-    if (!(l5 > 1e-280)) l5 = 1e-280;  // radial ray: the force term underflows to zero, as it should
-    F.L = pow(l5, 0.2);
-    const double iL = 1.0 / F.L;
-    F.qh = iL * iL;
+    if (!(l5 > 1e-30)) l5 = 1e-30;    // (near-)radial ray: the force is ~1e-30 of anything else either way
+    const double iL = inv_fifth_root(l5);
+    const double iL2 = iL * iL;
+    F.L = l5 * (iL2 * iL2);           // a^(1/5) = a * a^(-4/5)
+    F.iL = iL;
+    F.qh = iL2;
     const double s2 = n0 * n0 + n2 * n2;
     if (!(h2 > 1e-280) || !(s2 > 1e-28 * h2)) {
         // radial ray (no plane) or a plane that IS the disk plane: f1 = cam/|cam|, f2 any
@@ -205,14 +235,14 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
     F.ysign = -1;
 }
 
-// traceRay's setup (src/Raytracer.hs:69-75): ray, h2 = |pos x vel|^2, acc = 0
-BSB_HD void ray_init(const FrameParams &P, int x, int y, RayState &s)
+// traceRay's setup (src/Raytracer.hs:69-75): ray, h2 = |pos x vel|^2, acc = 0.  The frame F is
+// handed back so the caller can keep it (shared memory in the kernels) for ray_finish.
+BSB_HD void ray_init(const FrameParams &P, int x, int y, RayState &s, RayFrame &F)
 {
     double dir[3];
-    RayFrame F;
     ray_direction(P, x, y, dir);
     ray_frame(P, dir, F);
-    const double iL = 1.0 / F.L;
+    const double iL = F.iL;
     s.u = (P.cam[0] * F.f1[0] + P.cam[1] * F.f1[1] + P.cam[2] * F.f1[2]) * iL;
     s.v = (P.cam[0] * F.f2[0] + P.cam[1] * F.f2[1] + P.cam[2] * F.f2[2]) * iL;
     s.du = (dir[0] * F.f1[0] + dir[1] * F.f1[1] + dir[2] * F.f1[2]) * iL;
@@ -429,9 +459,10 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, 
             if (d2 <= r2max) {
                 const double ex = exp(a_mag * (950.0 - (double)st.mag) - d2 / two_w2);        // :113
                 const double val = (ex < 1.0 ? ex : 1.0) * P.star_intensity;                  // :112
-                double c[3];
-                hsi_to_rgb(st.hue, P.star_saturation * st.sat, val, c);                       // :114
-                rgb[0] += c[0]; rgb[1] += c[1]; rgb[2] += c[2];                               // :115 foldl'
+                // :114 toPixelRGB (PixelHSI hue (saturation*sat) val): channel = val (1 + S k_c)
+                rgb[0] += val * fma_(P.star_saturation, st.kr, 1.0);                          // :115 foldl'
+                rgb[1] += val * fma_(P.star_saturation, st.kg, 1.0);
+                rgb[2] += val * fma_(P.star_saturation, st.kb, 1.0);
                 hits++;
             }
         }
@@ -445,8 +476,8 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, 
 }
 
 // Finish a terminated ray: findColor's Bottom cases (src/Raytracer.hs:93-95) + dropAlpha (:75).
-// (x, y) are the ray's grid coordinates, needed to rebuild e2 for the 3-D exit velocity.
-BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, int x, int y,
+// F is the frame ray_init produced for this ray (needed for the 3-D exit velocity).
+BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, const RayFrame &F,
                            const RayState &s, double rgb[3])
 {
     uint32_t hits = 0;
@@ -454,10 +485,6 @@ BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, i
     if (s.status == kSky) {
         double c[4] = { 0, 0, 0, 1.0 };
         if (P.tree.n_stars > 0) {
-            double dir[3];
-            RayFrame F;
-            ray_direction(P, x, y, dir);
-            ray_frame(P, dir, F);
             const double vu = s.du * F.L, vv = s.dv * F.L;   // :94 the pre-step velocity, unscaled
             const double vel[3] = { fma_(vu, F.f1[0], vv * F.f2[0]), fma_(vu, F.f1[1], vv * F.f2[1]),
                                     fma_(vu, F.f1[2], vv * F.f2[2]) };

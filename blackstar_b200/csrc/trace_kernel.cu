@@ -45,6 +45,26 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
     return v;
 }
 
+// The ray's orbital-plane frame is needed again when the ray is finished (3-D exit velocity
+// for the sky lookup).  It is parked in shared memory meanwhile instead of being recomputed
+// (two divisions, three square roots and a fifth root) or held in registers.
+struct FrameStore { double v[8][kTraceThreads]; };   // f1[3], f2[3], L, (unused)
+
+__device__ __forceinline__ void park_frame(FrameStore &fs, const RayFrame &F)
+{
+    const int t = threadIdx.x;
+    fs.v[0][t] = F.f1[0]; fs.v[1][t] = F.f1[1]; fs.v[2][t] = F.f1[2];
+    fs.v[3][t] = F.f2[0]; fs.v[4][t] = F.f2[1]; fs.v[5][t] = F.f2[2];
+    fs.v[6][t] = F.L;
+}
+__device__ __forceinline__ void fetch_frame(const FrameStore &fs, RayFrame &F)
+{
+    const int t = threadIdx.x;
+    F.f1[0] = fs.v[0][t]; F.f1[1] = fs.v[1][t]; F.f1[2] = fs.v[2][t];
+    F.f2[0] = fs.v[3][t]; F.f2[1] = fs.v[4][t]; F.f2[2] = fs.v[5][t];
+    F.L = fs.v[6][t];
+}
+
 // lane -> ray coordinates inside tile `tile`
 template <bool SS>
 __device__ __forceinline__ void tile_coords(const FrameParams &P, unsigned tile, int lane, int &ox, int &oy,
@@ -80,6 +100,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB)
 trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ out, TraceCounters *ctr)
 {
     __shared__ double s_top[kSmemTreeNodes];
+    __shared__ FrameStore s_frames;
     int n_top;
     stage_tree_top(P, s_top, n_top);
 
@@ -105,9 +126,12 @@ trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ o
         double rgb[3] = { 0.0, 0.0, 0.0 };
         if (valid) {
             RayState s;
-            ray_init(P, gx, gy, s);
+            RayFrame F;
+            ray_init(P, gx, gy, s, F);
+            park_frame(s_frames, F);
             ray_advance(P, s, 0xffffffffu);
-            my_hits += ray_finish(P, s_top, n_top, gx, gy, s, rgb);
+            fetch_frame(s_frames, F);
+            my_hits += ray_finish(P, s_top, n_top, F, s, rgb);
             my_steps += s.steps;
             my_capped += (s.status == kCapped);
         }
@@ -141,6 +165,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3)
 trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ out, TraceCounters *ctr)
 {
     __shared__ double s_top[kSmemTreeNodes];
+    __shared__ FrameStore s_frames;
     int n_top;
     stage_tree_top(P, s_top, n_top);
 
@@ -178,7 +203,9 @@ trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ 
             double rgb[3] = { 0.0, 0.0, 0.0 };
             const bool fin = unit_done && occupied && valid;
             if (fin) {
-                my_hits += ray_finish(P, s_top, n_top, gx, gy, s, rgb);
+                RayFrame F;
+                fetch_frame(s_frames, F);
+                my_hits += ray_finish(P, s_top, n_top, F, s, rgb);
                 my_steps += s.steps;
                 my_capped += (s.status == kCapped);
             }
@@ -210,7 +237,11 @@ trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ 
                         tile_coords<SS>(P, tile, slot * LPU + (lane & (LPU - 1)), ox, oy, gx, gy);
                         occupied = true;
                         valid = ox < P.W && oy < P.row1;
-                        if (valid) ray_init(P, gx, gy, s);
+                        if (valid) {
+                            RayFrame F;
+                            ray_init(P, gx, gy, s, F);
+                            park_frame(s_frames, F);
+                        }
                     }
                 }
             }
@@ -232,6 +263,24 @@ trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ 
         if (my_capped) atomicAdd(&ctr->capped, my_capped);
         if (my_hits) atomicAdd(&ctr->star_hits, my_hits);
     }
+}
+
+// ---- per-frame ray tables: vx[x] (x < W2) and vy[y] (y < H2), exact reference op order ----
+__global__ void ray_tables_kernel(const __grid_constant__ FrameParams P, double *vx, double *vy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.W2) vx[i] = pixel_vx(P, i);
+    if (i < P.H2) vy[i] = pixel_vy(P, i);
+}
+
+cudaError_t launch_ray_tables(const FrameParams &P_in, double *vx, double *vy, cudaStream_t stream)
+{
+    FrameParams P = P_in;
+    P.vx_tab = nullptr;
+    P.vy_tab = nullptr;
+    const int n = P.W2 > P.H2 ? P.W2 : P.H2;
+    ray_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, vx, vy);
+    return cudaGetLastError();
 }
 
 // ---- numerics self-test of the |pos|^-5 kernel primitive: max relative error of

@@ -138,7 +138,7 @@ class TiledFrame:
     def step(self, want_stats: bool = False):
         r0, r1 = self.tiles[self.rank]
         st = self.r.render_device(self.cfg, self.tile.data_ptr(), r0, r1, want_stats=want_stats)
-        self.launches += 1 if r1 > r0 else 0
+        self.launches += 2 if r1 > r0 else 0   # ray tables + trace
         gather_tiles(self.full, self.tile, self.tiles, self.rank, self.world)
         scn = self.cfg.scene
         if self.rank == 0 and scn.bloomStrength != 0:  # app/Main.hs:113

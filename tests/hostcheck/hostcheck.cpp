@@ -58,13 +58,14 @@ int hc_render(void *p, const bsb_camera *cam, const bsb_scene *scn, int row0, in
                 const int gx = P.ss ? 2 * ox + (sub >> 1) : ox;
                 const int gy = P.ss ? 2 * oy + (sub & 1) : oy;
                 RayState s;
-                ray_init(P, gx, gy, s);
+                RayFrame F;
+                ray_init(P, gx, gy, s, F);
                 if (block_steps > 0) {
                     while (s.status == kAlive) ray_advance(P, s, (uint32_t)block_steps);
                 } else {
                     ray_advance(P, s, 0xffffffffu);
                 }
-                hits += ray_finish(P, P.tree.split, n_top, gx, gy, s, px[sub]);
+                hits += ray_finish(P, P.tree.split, n_top, F, s, px[sub]);
                 steps += s.steps;
             }
             double *o = out_rgb + ((size_t)(oy - row0) * P.W + ox) * 3;

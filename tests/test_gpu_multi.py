@@ -35,6 +35,6 @@ def test_render_full_is_identical_on_1_and_n_gpus(scenes_dir, scene, res):
             got = rk.do_render(cfg)
             st = rk.last_stats
             got8 = rk.do_render_srgb8(cfg)
-        assert st["n_gpus"] == k and st["launches"] == k + 2
+        assert st["n_gpus"] == k and st["launches"] == 2 * k + 2
         np.testing.assert_array_equal(got, ref)
         np.testing.assert_array_equal(got8, ref8)
