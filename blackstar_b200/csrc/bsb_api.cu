@@ -81,10 +81,12 @@ struct DeviceState {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // own_stream, or the caller's (device 0 only)
     // star map
-    double *d_split = nullptr;
-    uint32_t *d_leaf_off = nullptr;
+    float *d_top = nullptr;
+    double *d_rec = nullptr;
     StarRec *d_stars = nullptr;
+    uint32_t rec_off[4] = { 0, 0, 0, 0 };
     int depth = 0;
+    int top_levels = 0;
     int n_stars = 0;
     // per-launch counters
     TraceCounters *d_ctr = nullptr;
@@ -139,11 +141,11 @@ int ensure(bsb_ctx *ctx, T *&ptr, size_t &cap, size_t need)
 
 void free_tree(DeviceState &d)
 {
-    if (d.d_split) cudaFree(d.d_split);
-    if (d.d_leaf_off) cudaFree(d.d_leaf_off);
+    if (d.d_top) cudaFree(d.d_top);
+    if (d.d_rec) cudaFree(d.d_rec);
     if (d.d_stars) cudaFree(d.d_stars);
-    d.d_split = nullptr; d.d_leaf_off = nullptr; d.d_stars = nullptr;
-    d.depth = 0; d.n_stars = 0;
+    d.d_top = nullptr; d.d_rec = nullptr; d.d_stars = nullptr;
+    d.depth = 0; d.top_levels = 0; d.n_stars = 0;
 }
 
 double ms_since(std::chrono::steady_clock::time_point t0)
@@ -158,11 +160,13 @@ int trace_async(bsb_ctx *ctx, DeviceState &d, const bsb_camera *cam, const bsb_s
     FrameParams P;
     const std::string msg = make_frame_params(*cam, *scn, row0, row1, P);
     if (!msg.empty()) return fail(ctx, BSB_ERR_INVALID, msg);
-    P.tree.split = d.d_split;
-    P.tree.leaf_off = d.d_leaf_off;
+    P.tree.top = d.d_top;
+    P.tree.rec = d.d_rec;
     P.tree.stars = d.d_stars;
     P.tree.depth = d.depth;
+    P.tree.top_levels = d.top_levels;
     P.tree.n_stars = d.n_stars;
+    for (int g = 0; g < 4; g++) P.tree.rec_off[g] = d.rec_off[g];
     BSB_CUDA(ctx, cudaSetDevice(d.dev));
     int rc = ensure(ctx, d.d_vx, d.vx_cap, (size_t)P.W2);
     if (rc) return rc;
@@ -358,18 +362,20 @@ extern "C" int bsb_set_stars(bsb_ctx *ctx, const bsb_star *stars, size_t n)
     if (n > 0 && !stars) return fail(ctx, BSB_ERR_INVALID, "bsb_set_stars: NULL star list");
     if (n > (size_t)1 << 28) return fail(ctx, BSB_ERR_INVALID, "bsb_set_stars: too many stars");
     HostStarTree t;
-    if (n > 0) build_star_tree(stars, n, 8, t);
+    if (n > 0) build_star_tree(stars, n, t);
     for (DeviceState &d : ctx->devs) {
         BSB_CUDA(ctx, cudaSetDevice(d.dev));
         BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
         free_tree(d);
         if (n == 0) continue;
-        BSB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d.d_split), t.split.size() * sizeof(double)));
-        BSB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d.d_leaf_off), t.leaf_off.size() * sizeof(uint32_t)));
+        BSB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d.d_top), t.top.size() * sizeof(float)));
+        BSB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d.d_rec), t.rec.size() * sizeof(double)));
         BSB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d.d_stars), t.stars.size() * sizeof(StarRec)));
-        BSB_CUDA(ctx, cudaMemcpy(d.d_split, t.split.data(), t.split.size() * sizeof(double), cudaMemcpyHostToDevice));
-        BSB_CUDA(ctx, cudaMemcpy(d.d_leaf_off, t.leaf_off.data(), t.leaf_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        BSB_CUDA(ctx, cudaMemcpy(d.d_top, t.top.data(), t.top.size() * sizeof(float), cudaMemcpyHostToDevice));
+        BSB_CUDA(ctx, cudaMemcpy(d.d_rec, t.rec.data(), t.rec.size() * sizeof(double), cudaMemcpyHostToDevice));
         BSB_CUDA(ctx, cudaMemcpy(d.d_stars, t.stars.data(), t.stars.size() * sizeof(StarRec), cudaMemcpyHostToDevice));
+        for (int g = 0; g < 4; g++) d.rec_off[g] = t.rec_off[g];
+        d.top_levels = t.top_levels;
         d.depth = t.depth;
         d.n_stars = (int)n;
     }

@@ -31,20 +31,29 @@ struct StarRec {
 static_assert(sizeof(StarRec) == 64, "StarRec is 64 bytes");
 
 // Bucketed k-d tree over the unit-sphere star positions (DESIGN.md "star map").
-//   internal nodes: implicit complete binary tree in heap order, n_internal = 2^depth - 1;
-//   split[i] holds the split coordinate with the split axis (0,1,2) in the two lowest
-//   mantissa bits; points with coord <= split go left, >= split go right.
-//   leaf l (0 <= l < 2^depth) owns stars [leaf_off[l], leaf_off[l+1]).
+//   2^depth leaves of exactly kLeafSlots star records each (padded with records that can never
+//   be in range), so a leaf is one unrolled burst of independent loads and needs no offsets.
+//   Split planes of an implicit complete binary tree; node (d, i) = i-th node of depth d,
+//   children (d+1, 2i) and (d+1, 2i+1); points with coord <= split go left, >= split go right.
+//   Levels 0 .. top_levels-1: `top`, heap order, FLOAT with the split axis in the two lowest
+//     mantissa bits -- 2^13 - 1 nodes = 32 KB, staged in shared memory by every CTA.
+//   Deeper levels in groups of three: one 64-byte record per 3-level subtree (local heap order
+//     1..7, doubles with the axis in the two lowest mantissa bits), so that three levels cost ONE
+//     dependent L2 access instead of three.  Group g starts at record rec_off[g].
 struct StarTreeDev {
-    const double *split;
-    const uint32_t *leaf_off;
+    const float *top;
+    const double *rec;
     const StarRec *stars;
-    int32_t depth;
+    int32_t depth;        // leaves live at this depth
+    int32_t top_levels;   // T; (depth - T) is a multiple of 3
     int32_t n_stars;
+    int32_t pad;
+    uint32_t rec_off[4];
 };
 
-constexpr int kSmemTreeLevels = 12;                       // top levels staged in shared memory
-constexpr int kSmemTreeNodes = (1 << kSmemTreeLevels) - 1; // 4095 doubles = 32 KB
+constexpr int kLeafSlots = 8;
+constexpr int kSmemTreeLevels = 13;                        // top levels staged in shared memory
+constexpr int kSmemTreeNodes = (1 << kSmemTreeLevels) - 1; // 8191 floats = 32 KB
 
 // Everything a ray needs that is constant over the frame.  Passed by value as a
 // __grid_constant__ kernel parameter (constant bank, warp-uniform loads).

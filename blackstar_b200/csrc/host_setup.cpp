@@ -132,14 +132,36 @@ struct Builder {
     const bsb_star *s;
     std::vector<uint32_t> idx;
     HostStarTree *t;
-    int depth;
+    int depth, T;
 
-    void rec(size_t node, int level, size_t lo, size_t hi)
+    void store_split(int d, size_t i, double sv, int axis)
     {
-        if (level == depth) {
-            const size_t leaf = node - ((size_t(1) << depth) - 1);
-            t->leaf_off[leaf] = (uint32_t)lo;
-            t->leaf_off[leaf + 1] = (uint32_t)hi;  // leaves are visited left to right
+        if (d < T) {
+            float f = (float)sv;
+            uint32_t bits;
+            std::memcpy(&bits, &f, 4);
+            bits = (bits & ~uint32_t(3)) | uint32_t(axis);
+            std::memcpy(&t->top[(size_t(1) << d) - 1 + i], &bits, 4);
+        } else {
+            const int g = (d - T) / 3, l = (d - T) - 3 * g;
+            const size_t blk = i >> l, local = (size_t(1) << l) + (i & ((size_t(1) << l) - 1));
+            uint64_t bits;
+            std::memcpy(&bits, &sv, 8);
+            bits = (bits & ~uint64_t(3)) | uint64_t(axis);
+            std::memcpy(&t->rec[(size_t(t->rec_off[g]) + blk) * 8 + local], &bits, 8);
+        }
+    }
+
+    void rec(int d, size_t i, size_t lo, size_t hi)
+    {
+        if (d == depth) {
+            StarRec *slot = &t->stars[i * kLeafSlots];
+            for (size_t k = lo; k < hi; k++) {
+                const bsb_star &st = s[idx[k]];
+                double k3[3];
+                hue_coefficients(st.hue, k3);
+                slot[k - lo] = StarRec{ st.pos[0], st.pos[1], st.pos[2], st.sat * k3[0], st.sat * k3[1], st.sat * k3[2], st.mag, 0, 0.0 };
+            }
             return;
         }
         int axis = 0;
@@ -163,35 +185,38 @@ struct Builder {
                              [sp, ax](uint32_t a, uint32_t b) { return sp[a].pos[ax] < sp[b].pos[ax]; });
             sv = s[idx[mid]].pos[axis];
         }
-        uint64_t bits;
-        std::memcpy(&bits, &sv, 8);
-        bits = (bits & ~uint64_t(3)) | uint64_t(axis);
-        std::memcpy(&t->split[node], &bits, 8);
-        rec(2 * node + 1, level + 1, lo, mid);
-        rec(2 * node + 2, level + 1, mid, hi);
+        store_split(d, i, sv, axis);
+        rec(d + 1, 2 * i, lo, mid);
+        rec(d + 1, 2 * i + 1, mid, hi);
     }
 };
 
 }  // namespace
 
-void build_star_tree(const bsb_star *stars, size_t n, int leaf_size, HostStarTree &out)
+void build_star_tree(const bsb_star *stars, size_t n, HostStarTree &out)
 {
-    if (leaf_size < 1) leaf_size = 1;
     int depth = 0;
-    while ((size_t(leaf_size) << depth) < n && depth < 24) depth++;
+    while ((size_t(kLeafSlots) << depth) < n && depth < 25) depth++;
+    // top levels (shared memory) + groups of three levels below them
+    int T = depth;
+    if (depth > kSmemTreeLevels) {
+        const int groups = (depth - kSmemTreeLevels + 2) / 3;
+        T = depth - 3 * groups;
+    }
     out.depth = depth;
-    out.split.assign((size_t(1) << depth) - 1 + 1, 0.0);  // +1: never zero-sized
-    out.leaf_off.assign((size_t(1) << depth) + 1, 0u);
-    Builder b{ stars, std::vector<uint32_t>(n), &out, depth };
+    out.top_levels = T;
+    out.top.assign((size_t(1) << T) - 1 + 1, 0.0f);  // +1: never zero-sized
+    size_t n_rec = 0;
+    for (int g = 0; T + 3 * g < depth; g++) {
+        out.rec_off[g] = (uint32_t)n_rec;
+        n_rec += size_t(1) << (T + 3 * g);
+    }
+    out.rec.assign(n_rec * 8 + 8, 0.0);
+    // padding record: far outside the unit sphere, never within the lookup radius
+    out.stars.assign((size_t(1) << depth) * kLeafSlots, StarRec{ 4.0, 4.0, 4.0, 0.0, 0.0, 0.0, 0, 0, 0.0 });
+    Builder b{ stars, std::vector<uint32_t>(n), &out, depth, T };
     std::iota(b.idx.begin(), b.idx.end(), 0u);
     b.rec(0, 0, 0, n);
-    out.stars.resize(n);
-    for (size_t k = 0; k < n; k++) {
-        const bsb_star &s = stars[b.idx[k]];
-        double k3[3];
-        hue_coefficients(s.hue, k3);
-        out.stars[k] = StarRec{ s.pos[0], s.pos[1], s.pos[2], s.sat * k3[0], s.sat * k3[1], s.sat * k3[2], s.mag, 0, 0.0 };
-    }
 }
 
 // ------------------------------------------------------------------ PPM catalogue

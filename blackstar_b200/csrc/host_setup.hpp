@@ -18,14 +18,16 @@ std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int r
                               FrameParams &P);
 
 struct HostStarTree {
-    std::vector<double> split;       // 2^depth - 1 entries, axis in the 2 low mantissa bits
-    std::vector<uint32_t> leaf_off;  // 2^depth + 1 entries
-    std::vector<StarRec> stars;      // leaf order
+    std::vector<float> top;          // 2^top_levels - 1 entries (heap order), axis in the 2 low mantissa bits
+    std::vector<double> rec;         // 8 doubles per 3-level subtree below the top
+    std::vector<StarRec> stars;      // kLeafSlots records per leaf, padded
+    uint32_t rec_off[4] = { 0, 0, 0, 0 };
     int depth = 0;
+    int top_levels = 0;
 };
 
-// Median-split k-d tree with buckets of <= ~leaf_size stars; widest-extent split axis.
-void build_star_tree(const bsb_star *stars, size_t n, int leaf_size, HostStarTree &out);
+// Median-split k-d tree (widest-extent axis) with 2^depth leaves of <= kLeafSlots stars.
+void build_star_tree(const bsb_star *stars, size_t n, HostStarTree &out);
 
 // StarMap.readMap + starColor' : PPM binary catalogue -> flat star list.
 bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err);

@@ -409,9 +409,8 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 }
 
 // ---- sky: StarMap.starLookup (src/StarMap.hs:93-115) over the bucketed k-d tree --------
-// `top` points at the tree's top levels (shared memory on the device), `n_top` nodes of it.
-BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, const double vel[3],
-                            double rgb[3])
+// `top` points at the tree's top levels (shared memory on the device).
+BSB_HD uint32_t star_lookup(const FrameParams &P, const float *top, const double vel[3], double rgb[3])
 {
     rgb[0] = rgb[1] = rgb[2] = 0.0;
     const StarTreeDev &T = P.tree;
@@ -430,30 +429,48 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, 
     const double w = 0.0005;                      // :101
     const double radius = 3 * w;                  // :104
     const double r2max = mul_rn(radius, radius);  // kdt: distSqr p q <= radius*radius
-    const double rprune = radius + 1e-12;         // split values carry the axis in 2 mantissa bits
+    // pruning margins: the stored split planes are rounded (float / 2 stolen mantissa bits), the
+    // exact inclusion test below decides membership
+    const double prune_top = radius + 2e-6, prune_rec = radius + 1e-12;
     const double a_mag = 0.013862943611198907;    // :108 log 2 / dynamic (= ln2/50, correctly rounded)
     const double two_w2 = 2 * (w * w);            // :113 d2 / (2*w^2)
-    const int n_internal = (1 << T.depth) - 1;
+    const int D = T.depth, TL = T.top_levels;
     uint32_t hits = 0;
-    int stack[24];
+    uint32_t stack[32];                           // (depth << 26) | index within the level
     int sp = 0;
-    int node = 0;
+    int d = 0;
+    uint32_t i = 0;
     for (;;) {
-        while (node < n_internal) {
-            union { double d; uint64_t b; } sv;
-            sv.d = (node < n_top) ? top[node] : T.split[node];
-            const int axis = (int)(sv.b & 3ull);
+        while (d < D) {
+            double sv, margin;
+            int axis;
+            if (d < TL) {
+                const float f = top[(1u << d) - 1u + i];
+                union { float f; uint32_t b; } cv;
+                cv.f = f;
+                axis = (int)(cv.b & 3u);
+                sv = (double)f;
+                margin = prune_top;
+            } else {
+                const int g = (d - TL) / 3, l = (d - TL) - 3 * g;
+                const uint32_t blk = i >> l, local = (1u << l) + (i & ((1u << l) - 1u));
+                union { double d; uint64_t b; } cv;
+                cv.d = T.rec[((size_t)T.rec_off[g] + blk) * 8 + local];
+                axis = (int)(cv.b & 3ull);
+                sv = cv.d;
+                margin = prune_rec;
+            }
             const double qa = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
-            const double diff = qa - sv.d;
-            const int near = 2 * node + 1 + (diff > 0.0 ? 1 : 0);
-            const int far = 2 * node + 1 + (diff > 0.0 ? 0 : 1);
-            if (fabs(diff) <= rprune) stack[sp++] = far;
-            node = near;
+            const double diff = qa - sv;
+            const uint32_t right = diff > 0.0 ? 1u : 0u;
+            if (fabs(diff) <= margin) stack[sp++] = ((uint32_t)(d + 1) << 26) | (2u * i + (1u - right));
+            i = 2u * i + right;
+            d++;
         }
-        const int leaf = node - n_internal;
-        const uint32_t b0 = T.leaf_off[leaf], b1 = T.leaf_off[leaf + 1];
-        for (uint32_t j = b0; j < b1; j++) {
-            const StarRec &st = T.stars[j];
+        const StarRec *leaf = T.stars + (size_t)i * kLeafSlots;
+#pragma unroll
+        for (int j = 0; j < kLeafSlots; j++) {
+            const StarRec &st = leaf[j];
             const double dx = sub_rn(st.x, n0), dy = sub_rn(st.y, n1), dz = sub_rn(st.z, n2);
             const double d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)); // :107 qd
             if (d2 <= r2max) {
@@ -467,7 +484,9 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, 
             }
         }
         if (sp == 0) break;
-        node = stack[--sp];
+        const uint32_t e = stack[--sp];
+        d = (int)(e >> 26);
+        i = e & 0x03ffffffu;
     }
     rgb[0] = rgb[0] < 1.0 ? rgb[0] : 1.0;          // :115 fmap (min 1)
     rgb[1] = rgb[1] < 1.0 ? rgb[1] : 1.0;
@@ -477,8 +496,8 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const double *top, int n_top, 
 
 // Finish a terminated ray: findColor's Bottom cases (src/Raytracer.hs:93-95) + dropAlpha (:75).
 // F is the frame ray_init produced for this ray (needed for the 3-D exit velocity).
-BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, const RayFrame &F,
-                           const RayState &s, double rgb[3])
+BSB_HD uint32_t ray_finish(const FrameParams &P, const float *top, const RayFrame &F, const RayState &s,
+                           double rgb[3])
 {
     uint32_t hits = 0;
     double acc[4] = { s.acc[0], s.acc[1], s.acc[2], s.acc[3] };
@@ -488,7 +507,7 @@ BSB_HD uint32_t ray_finish(const FrameParams &P, const double *top, int n_top, c
             const double vu = s.du * F.L, vv = s.dv * F.L;   // :94 the pre-step velocity, unscaled
             const double vel[3] = { fma_(vu, F.f1[0], vv * F.f2[0]), fma_(vu, F.f1[1], vv * F.f2[1]),
                                     fma_(vu, F.f1[2], vv * F.f2[2]) };
-            hits = star_lookup(P, top, n_top, vel, c);
+            hits = star_lookup(P, top, vel, c);
         }
         blend_under(acc, c);
     }

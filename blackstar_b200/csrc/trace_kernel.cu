@@ -27,13 +27,11 @@ namespace bsb {
 constexpr int kTraceThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ void stage_tree_top(const FrameParams &P, double *s_top, int &n_top)
+__device__ __forceinline__ void stage_tree_top(const FrameParams &P, float *s_top)
 {
-    n_top = 0;
     if (P.tree.n_stars > 0) {
-        const int n_internal = (1 << P.tree.depth) - 1;
-        n_top = n_internal < kSmemTreeNodes ? n_internal : kSmemTreeNodes;
-        for (int i = threadIdx.x; i < n_top; i += blockDim.x) s_top[i] = P.tree.split[i];
+        const int n_top = (1 << P.tree.top_levels) - 1;
+        for (int i = threadIdx.x; i < n_top; i += blockDim.x) s_top[i] = P.tree.top[i];
     }
     __syncthreads();
 }
@@ -99,10 +97,9 @@ template <bool SS, int MINB>
 __global__ void __launch_bounds__(kTraceThreads, MINB)
 trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ out, TraceCounters *ctr)
 {
-    __shared__ double s_top[kSmemTreeNodes];
+    __shared__ float s_top[kSmemTreeNodes + 1];
     __shared__ FrameStore s_frames;
-    int n_top;
-    stage_tree_top(P, s_top, n_top);
+    stage_tree_top(P, s_top);
 
     const int lane = threadIdx.x & 31;
     unsigned long long my_steps = 0, my_capped = 0, my_hits = 0;
@@ -131,7 +128,7 @@ trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ o
             park_frame(s_frames, F);
             ray_advance(P, s, 0xffffffffu);
             fetch_frame(s_frames, F);
-            my_hits += ray_finish(P, s_top, n_top, F, s, rgb);
+            my_hits += ray_finish(P, s_top, F, s, rgb);
             my_steps += s.steps;
             my_capped += (s.status == kCapped);
         }
@@ -164,10 +161,9 @@ template <bool SS, int kBlockSteps, int kRefillMin>
 __global__ void __launch_bounds__(kTraceThreads, 3)
 trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ out, TraceCounters *ctr)
 {
-    __shared__ double s_top[kSmemTreeNodes];
+    __shared__ float s_top[kSmemTreeNodes + 1];
     __shared__ FrameStore s_frames;
-    int n_top;
-    stage_tree_top(P, s_top, n_top);
+    stage_tree_top(P, s_top);
 
     constexpr int U = SS ? 8 : 32;           // units per warp
     constexpr int LPU = 32 / U;              // lanes per unit
@@ -205,7 +201,7 @@ trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ 
             if (fin) {
                 RayFrame F;
                 fetch_frame(s_frames, F);
-                my_hits += ray_finish(P, s_top, n_top, F, s, rgb);
+                my_hits += ray_finish(P, s_top, F, s, rgb);
                 my_steps += s.steps;
                 my_capped += (s.status == kCapped);
             }

@@ -17,13 +17,15 @@ struct HcCtx {
 
 extern "C" {
 
-void *hc_create(const bsb_star *stars, size_t n, int leaf_size)
+void *hc_create(const bsb_star *stars, size_t n, int /*unused*/)
 {
     HcCtx *c = new HcCtx();
     c->n = n;
-    if (n) build_star_tree(stars, n, leaf_size, c->tree);
+    if (n) build_star_tree(stars, n, c->tree);
     return c;
 }
+
+int hc_tree_top_levels(void *p) { return static_cast<HcCtx *>(p)->tree.top_levels; }
 
 void hc_destroy(void *p) { delete static_cast<HcCtx *>(p); }
 
@@ -31,11 +33,13 @@ int hc_tree_depth(void *p) { return static_cast<HcCtx *>(p)->tree.depth; }
 
 static void attach(HcCtx *c, FrameParams &P)
 {
-    P.tree.split = c->tree.split.data();
-    P.tree.leaf_off = c->tree.leaf_off.data();
+    P.tree.top = c->tree.top.data();
+    P.tree.rec = c->tree.rec.data();
     P.tree.stars = c->tree.stars.data();
     P.tree.depth = c->tree.depth;
+    P.tree.top_levels = c->tree.top_levels;
     P.tree.n_stars = (int)c->n;
+    for (int g = 0; g < 4; g++) P.tree.rec_off[g] = c->tree.rec_off[g];
 }
 
 // Renders rows [row0,row1) of the final image exactly as the tiles kernel does per lane.
@@ -47,8 +51,6 @@ int hc_render(void *p, const bsb_camera *cam, const bsb_scene *scn, int row0, in
     FrameParams P;
     if (!make_frame_params(*cam, *scn, row0, row1, P).empty()) return 1;
     attach(c, P);
-    const int n_internal = (1 << P.tree.depth) - 1;
-    const int n_top = c->n ? (n_internal < kSmemTreeNodes ? n_internal : kSmemTreeNodes) : 0;
     unsigned long long steps = 0, hits = 0;
     for (int oy = row0; oy < row1; oy++)
         for (int ox = 0; ox < P.W; ox++) {
@@ -65,7 +67,7 @@ int hc_render(void *p, const bsb_camera *cam, const bsb_scene *scn, int row0, in
                 } else {
                     ray_advance(P, s, 0xffffffffu);
                 }
-                hits += ray_finish(P, P.tree.split, n_top, F, s, px[sub]);
+                hits += ray_finish(P, P.tree.top, F, s, px[sub]);
                 steps += s.steps;
             }
             double *o = out_rgb + ((size_t)(oy - row0) * P.W + ox) * 3;
@@ -85,9 +87,7 @@ void hc_star_lookup(void *p, double intensity, double saturation, const double v
     attach(c, P);
     P.star_intensity = intensity;
     P.star_saturation = saturation;
-    const int n_internal = (1 << P.tree.depth) - 1;
-    const int n_top = c->n ? (n_internal < kSmemTreeNodes ? n_internal : kSmemTreeNodes) : 0;
-    *hits = star_lookup(P, P.tree.split, n_top, vel, rgb);
+    *hits = star_lookup(P, P.tree.top, vel, rgb);
 }
 
 double hc_rinv5(double q) { return rinv5(q); }

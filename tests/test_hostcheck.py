@@ -72,32 +72,38 @@ def test_every_scene_matches_oracle(hc, scenes_dir, scene):
     assert steps_b == steps
 
 
-def test_star_lookup_matches_oracle_and_brute_force(hc, small_stars):
-    tree = po.Tree(small_stars)
+@pytest.mark.parametrize("n_stars,depth,top", [(20000, 12, 12), (100000, 14, 11), (200000, 15, 12),
+                                               (468861, 16, 13), (1100000, 18, 12)])
+def test_star_lookup_matches_oracle_and_brute_force(hc, n_stars, depth, top):
+    # tree shapes: all levels in the shared-memory part / one and two groups of 3-level records
+    hc.hc_tree_top_levels.argtypes = [ctypes.c_void_p]
+    stars = starmap.synthetic_stars(n_stars, seed=17)
+    tree = po.Tree(stars) if n_stars <= 200000 else None   # the restated kdt build is O(n log^2 n)
     rng = np.random.default_rng(4)
-    for leaf in (1, 8, 64):
-        h_ = hc.hc_create(small_stars.ctypes.data, len(small_stars), leaf)
-        try:
-            nonzero = 0
-            for k in range(400):
-                if k % 2:
-                    v = small_stars["pos"][rng.integers(len(small_stars))] + rng.normal(0, 0.0007, 3)
-                else:
-                    v = rng.normal(0, 1, 3)
-                v = np.ascontiguousarray(v * rng.uniform(0.5, 2.0))  # lookup normalises (StarMap.hs:103)
-                got = np.zeros(3)
-                hits = ctypes.c_uint()
-                hc.hc_star_lookup(h_, 0.7, 1.3, v.ctypes.data, got.ctypes.data, ctypes.byref(hits))
-                want = tree.lookup(0.7, 1.3, v)
-                n = v / np.linalg.norm(v)
-                d = small_stars["pos"] - n
-                d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
-                assert hits.value == int((d2 <= 0.0015 * 0.0015).sum())
-                np.testing.assert_allclose(got, want, atol=1e-13)
-                nonzero += hits.value > 0
-            assert nonzero > 100
-        finally:
-            hc.hc_destroy(h_)
+    h_ = hc.hc_create(stars.ctypes.data, len(stars), 8)
+    try:
+        assert hc.hc_tree_depth(h_) == depth and hc.hc_tree_top_levels(h_) == top
+        nonzero = 0
+        pos = stars["pos"]
+        for k in range(300):
+            if k % 2:
+                v = pos[rng.integers(len(stars))] + rng.normal(0, 0.0007, 3)
+            else:
+                v = rng.normal(0, 1, 3)
+            v = np.ascontiguousarray(v * rng.uniform(0.5, 2.0))  # lookup normalises (StarMap.hs:103)
+            got = np.zeros(3)
+            hits = ctypes.c_uint()
+            hc.hc_star_lookup(h_, 0.7, 1.3, v.ctypes.data, got.ctypes.data, ctypes.byref(hits))
+            n = v / np.linalg.norm(v)
+            d = pos - n
+            d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            assert hits.value == int((d2 <= 0.0015 * 0.0015).sum())
+            if tree is not None:
+                np.testing.assert_allclose(got, tree.lookup(0.7, 1.3, v), atol=1e-13)
+            nonzero += hits.value > 0
+        assert nonzero > 100
+    finally:
+        hc.hc_destroy(h_)
 
 
 def test_tiny_and_empty_catalogues(hc, scenes_dir):
