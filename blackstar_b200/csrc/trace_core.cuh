@@ -68,18 +68,39 @@ BSB_HD double rsqrt_seed(double x)
 #endif
 }
 
+// Write the seed for x^-1/2 into the HIGH word of y, leaving its low word alone.  MUFU.RSQ64H
+// produces only a high word; letting `y` be one long-lived register pair whose low word was zeroed
+// once saves the "clear the low register" move ptxas otherwise emits for every seed.
+BSB_HD void rsqrt_seed_into(double &y, double x)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .f64 r;\n\t"
+        ".reg .b32 lo, hi, j1, j2;\n\t"
+        "rsqrt.approx.ftz.f64 r, %1;\n\t"
+        "mov.b64 {j1, hi}, r;\n\t"
+        "mov.b64 {lo, j2}, %0;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}" : "+d"(y) : "d"(x));
+#else
+    y = rsqrt_seed(x);
+#endif
+}
+
 // q^(-5/2), relative error ~1e-15.  With y0 = q^-1/2 (1+d) from the seed and m = q y0^2 = 1 - e:
 //   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + O(e^3))
 //            = y0^5 (7.875 - 11.25 m + 4.375 m^2),      |e| <~ 2^-19  =>  O(e^3) <~ 5e-17.
-// 7 DP instructions + 1 MUFU.
-BSB_HD double rinv5(double q)
+// 7 FP64 instructions + 1 MUFU.  `yh` is the seed holder; `k4` must hold 4.375 in a register
+// (an FP64 instruction takes one immediate, and only -11.25 / 7.875 fit as immediates there).
+BSB_HD double rinv5(double q, double &yh, double k4)
 {
-    const double y0 = rsqrt_seed(q);
+    rsqrt_seed_into(yh, q);
+    const double y0 = yh;
     const double y2 = y0 * y0;
     const double m = q * y2;
     const double y4 = y2 * y2;
     const double y5 = y4 * y0;
-    const double c = fma_(fma_(4.375, m, -11.25), m, 7.875);
+    const double c = fma_(fma_(k4, m, -11.25), m, 7.875);
     return y5 * c;
 }
 
@@ -311,21 +332,21 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
 }
 
 // One classical RK4 step of y' = f(y), f(vel,pos) = (-pos/|pos|^5, vel)  (src/Raytracer.hs:113-134)
-// from (u, v, du, dv) with q = u^2 + v^2 to (nu, nv, du, dv) with nq.  64 DP + 4 MUFU.
+// from (u, v, du, dv) with q = u^2 + v^2 to (nu, nv, du, dv) with nq.  60 FP64 + 4 MUFU.
 BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double &du, double &dv,
-                     double &nu, double &nv, double &nq)
+                     double &nu, double &nv, double &nq, double &yh, double k4)
 {
-    const double g1 = rinv5(q);
+    const double g1 = rinv5(q, yh, k4);
     const double a1u = g1 * u, a1v = g1 * v;                   // a_i hold MINUS the acceleration
     const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
-    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v));
+    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v), yh, k4);
     const double a2u = g2 * p2u, a2v = g2 * p2v;
     const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
-    const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v));
+    const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v), yh, k4);
     const double a3u = g3 * p3u, a3v = g3 * p3v;
     const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
     const double p4u = fma_(-P.hhh, a2u, peu), p4v = fma_(-P.hhh, a2v, pev);
-    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v));
+    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v), yh, k4);
     const double a4u = g4 * p4u, a4v = g4 * p4v;
     const double s23u = a2u + a3u, s23v = a2v + a3v;
     nu = fma_(-P.hsq6, a1u + s23u, peu);
@@ -338,29 +359,31 @@ BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double 
 // Advance one ray by at most `max_steps` RK4 steps (colorize', src/Raytracer.hs:80-85).
 // The reference takes the step first and then tests the OLD position; testing first and
 // skipping the (unused) last step gives the same result with one step less per ray.
-// The fast loop is unrolled twice over two register sets (A -> B -> A) so no state is copied;
-// per step it costs 64 DP + 4 MUFU + ~20 integer/control instructions.  Rare events
-// (termination, disk crossing, a radius whose high word equals a threshold's) leave it and are
-// resolved exactly outside.
+// On this machine every FP64 instruction occupies the issue port for two cycles and every other
+// instruction for one, so the fast loop is written for the smallest (2 x FP64 + others): it is
+// unrolled over two register sets (A -> B -> A, no state copies), has ONE exit test per step
+// (sign flip of u | radius outside the safe band of high words | step budget) and resolves what
+// happened -- exactly -- outside the loop.
 BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
     double ua = s.u, va = s.v, qa = s.q, du = s.du, dv = s.dv;
     double ub = ua, vb = va, qb = qa;
+    double yh = 0.0;                                            // seed holder: low word stays 0
+    const double k4 = P.k4375;
     // q > 0, so doubles order like their bit patterns.  Fast test on the high words: strictly
     // between the two thresholds' high words => neither the horizon nor the escape test fires.
     const long long qh = dbits(s.qh), qs = dbits(s.qs);
     const int lo_hi = hi32(s.qh) + 1;
     const unsigned span = (unsigned)(hi32(s.qs) - lo_hi);
-    int side = s.side;
-    const bool disk = P.disk_on != 0 && side != kSideNever;
+    const bool disk = P.disk_on != 0 && s.side != kSideNever;
     const int dmask = disk ? (int)0x80000000 : 0;              // sign-bit compare enabled?
     const uint32_t left = P.step_cap > s.steps ? P.step_cap - s.steps : 0u;
     const uint32_t budget = max_steps < left ? max_steps : left;
     uint32_t remaining = budget;
     int32_t status = kAlive;
     // `side` as a word whose sign bit is the sign u has on the current side of the disk plane
-    int side_word = (side == -1) ? (int)0x80000000 : 0;
-    bool first_is_zero = disk && side == kSideZero;             // signum y = 0 at the start (:96)
+    int side_word = (s.side == -1) ? (int)0x80000000 : 0;
+    bool first_is_zero = disk && s.side == kSideZero;           // signum y = 0 at the start (:96)
     for (;;) {
         // ---- exact tests on the current position (A)
         {
@@ -369,36 +392,39 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
             if (qi > qs) { status = kSky; break; }                 // :94 escaped
         }
         if (remaining == 0) break;
-        // ---- one careful step A -> B, then hand over to the fast loop
-        rk4_step(P, ua, va, qa, du, dv, ub, vb, qb);
-        remaining--;
-        int ev = 0;                                                // 1: crossing A->B, 2: crossing B->A
-        if (first_is_zero || (((hi32(ub) ^ side_word) & dmask) < 0)) ev = 1;
-        first_is_zero = false;
-        if (ev == 0) {
+        bool newest_is_b;
+        if (first_is_zero) {
+            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);       // rare: the camera sits in the disk plane
+            remaining--;
+            newest_is_b = true;
+        } else {
             for (;;) {
-                // B is current
-                if ((unsigned)(hi32(qb) - lo_hi) >= span || remaining == 0) { ua = ub; va = vb; qa = qb; break; }
-                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa);
+                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);
                 remaining--;
-                if (((hi32(ua) ^ side_word) & dmask) < 0) { ev = 2; break; }
-                // A is current
-                if ((unsigned)(hi32(qa) - lo_hi) >= span || remaining == 0) break;
-                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb);
+                if (((((hi32(ub) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qb) - lo_hi) >= span) | (remaining == 0)) != 0) {
+                    newest_is_b = true;
+                    break;
+                }
+                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, k4);
                 remaining--;
-                if (((hi32(ub) ^ side_word) & dmask) < 0) { ev = 1; break; }
+                if (((((hi32(ua) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qa) - lo_hi) >= span) | (remaining == 0)) != 0) {
+                    newest_is_b = false;
+                    break;
+                }
             }
         }
-        if (ev != 0) {
-            // old position o, new position w
-            const double uo = ev == 1 ? ua : ub, qo = ev == 1 ? qa : qb;
-            const double uw = ev == 1 ? ub : ua, vw = ev == 1 ? vb : va, qw = ev == 1 ? qb : qa;
-            // :102 r2ave = (y' r2 - y r2') / (y' - y); f1y cancels, 1/qh = L^2 restores the scale
+        // old position o, new position w
+        const double uo = newest_is_b ? ua : ub, qo = newest_is_b ? qa : qb;
+        const double uw = newest_is_b ? ub : ua, vw = newest_is_b ? vb : va, qw = newest_is_b ? qb : qa;
+        if (first_is_zero || (((hi32(uw) ^ side_word) & dmask) < 0)) {
+            // disk-plane crossing (:96); :102 r2ave = (y' r2 - y r2') / (y' - y): f1y cancels,
+            // 1/qh = L^2 restores the scale
             const double r2ave = ((uw * qo - uo * qw) / (uw - uo)) / s.qh;
             if (r2ave > P.din2 && r2ave < P.dout2) disk_layer(P, r2ave, s.acc);   // :97-98
             side_word = hi32(uw) & (int)0x80000000;
-            ua = uw; va = vw; qa = qw;
+            first_is_zero = false;
         }
+        ua = uw; va = vw; qa = qw;
     }
     const uint32_t n = budget - remaining;
     if (status == kAlive && s.steps + n >= P.step_cap) status = kCapped;

@@ -288,7 +288,8 @@ __global__ void rinv5_selftest_kernel(double q_lo, double q_hi, int n, double *m
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double q = q_lo * exp(lr * ((double)i + 0.5) / (double)n);
         const double ref = pow(q, -2.5);
-        const double got = rinv5(q);
+        double yh = 0.0;
+        const double got = rinv5(q, yh, 4.375);
         worst = fmax(worst, fabs(got - ref) / ref);
         const double y0 = rsqrt_seed(q);
         worst_seed = fmax(worst_seed, fabs(fma(-q * y0, y0, 1.0)));
@@ -316,7 +317,8 @@ static int persistent_grid(K kernel, int n_sms)
 }
 
 // variant: 0 = tiles, 1 = refill(block 16, min 8 lanes), 2 = refill(block 8, min 4), 3 = refill(block 32, min 8),
-//          4 = tiles compiled for 4 CTAs/SM (64 registers), 5 = 4 + staggered warp start
+//          4 = tiles compiled for 4 CTAs/SM (64 registers), 5 = 4 + staggered warp start,
+//          6 = tiles compiled for 2 CTAs/SM (<= 128 registers: every loop constant stays in a register)
 cudaError_t launch_trace(const FrameParams &P_in, float4 *out, TraceCounters *ctr, int n_sms, int variant,
                          cudaStream_t stream)
 {
@@ -344,6 +346,7 @@ cudaError_t launch_trace(const FrameParams &P_in, float4 *out, TraceCounters *ct
         case 2: BSB_LAUNCH((trace_refill_kernel<true, 8, 1>)); break;
         case 3: BSB_LAUNCH((trace_refill_kernel<true, 32, 2>)); break;
         case 4: BSB_LAUNCH((trace_tiles_kernel<true, 4>)); break;
+        case 6: BSB_LAUNCH((trace_tiles_kernel<true, 2>)); break;
         default: BSB_LAUNCH((trace_tiles_kernel<true, 3>)); break;
         }
     } else {
@@ -352,6 +355,7 @@ cudaError_t launch_trace(const FrameParams &P_in, float4 *out, TraceCounters *ct
         case 2: BSB_LAUNCH((trace_refill_kernel<false, 8, 4>)); break;
         case 3: BSB_LAUNCH((trace_refill_kernel<false, 32, 8>)); break;
         case 4: BSB_LAUNCH((trace_tiles_kernel<false, 4>)); break;
+        case 6: BSB_LAUNCH((trace_tiles_kernel<false, 2>)); break;
         default: BSB_LAUNCH((trace_tiles_kernel<false, 3>)); break;
         }
     }

@@ -90,6 +90,6 @@ void hc_star_lookup(void *p, double intensity, double saturation, const double v
     *hits = star_lookup(P, P.tree.top, vel, rgb);
 }
 
-double hc_rinv5(double q) { return rinv5(q); }
+double hc_rinv5(double q) { double yh = 0.0; return rinv5(q, yh, 4.375); }
 
 }  // extern "C"
