@@ -107,7 +107,7 @@ struct DeviceState {
 struct bsb_ctx {
     std::vector<DeviceState> devs;
     std::string err;
-    int trace_variant = 4;  // tiles schedule, 64-register build (4 CTAs/SM): fastest measured (profiles/)
+    int trace_variant = 6;  // tiles schedule, <=128-register build (2 CTAs/SM): fastest measured (profiles/)
     size_t n_stars = 0;
     NcclApi nccl;
     std::vector<ncclComm_t> comms;

@@ -461,35 +461,48 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const float *top, const double
     const double a_mag = 0.013862943611198907;    // :108 log 2 / dynamic (= ln2/50, correctly rounded)
     const double two_w2 = 2 * (w * w);            // :113 d2 / (2*w^2)
     const int D = T.depth, TL = T.top_levels;
+    // the top levels hold FLOAT planes: walk them with single-precision compares (one issue cycle
+    // each instead of two); the margin covers the rounding of the plane and of the query
+    const float f0 = (float)n0, f1 = (float)n1, f2 = (float)n2;
+    const float fmargin = (float)prune_top;
     uint32_t hits = 0;
     uint32_t stack[32];                           // (depth << 26) | index within the level
     int sp = 0;
     int d = 0;
     uint32_t i = 0;
     for (;;) {
-        while (d < D) {
-            double sv, margin;
-            int axis;
-            if (d < TL) {
-                const float f = top[(1u << d) - 1u + i];
+        // ---- shared-memory levels: heap index n = 2^d - 1 + i
+        if (d < TL) {
+            uint32_t n = (1u << d) - 1u + i;
+            const uint32_t n_top = (1u << TL) - 1u;
+            do {
                 union { float f; uint32_t b; } cv;
-                cv.f = f;
-                axis = (int)(cv.b & 3u);
-                sv = (double)f;
-                margin = prune_top;
-            } else {
-                const int g = (d - TL) / 3, l = (d - TL) - 3 * g;
-                const uint32_t blk = i >> l, local = (1u << l) + (i & ((1u << l) - 1u));
-                union { double d; uint64_t b; } cv;
-                cv.d = T.rec[((size_t)T.rec_off[g] + blk) * 8 + local];
-                axis = (int)(cv.b & 3ull);
-                sv = cv.d;
-                margin = prune_rec;
-            }
+                cv.f = top[n];
+                const uint32_t axis = cv.b & 3u;
+                const float qa = axis == 0u ? f0 : (axis == 1u ? f1 : f2);
+                const float diff = qa - cv.f;
+                const uint32_t right = diff > 0.0f ? 1u : 0u;
+                if (fabsf(diff) <= fmargin) {
+                    const uint32_t far = 2u * n + 2u - right;             // heap index of the other child
+                    const int fd = d + 1;
+                    stack[sp++] = ((uint32_t)fd << 26) | (far - ((1u << fd) - 1u));
+                }
+                n = 2u * n + 1u + right;
+                d++;
+            } while (n < n_top);
+            i = n - ((1u << d) - 1u);
+        }
+        // ---- 3-level records below
+        while (d < D) {
+            const int g = (d - TL) / 3, l = (d - TL) - 3 * g;
+            const uint32_t blk = i >> l, local = (1u << l) + (i & ((1u << l) - 1u));
+            union { double d; uint64_t b; } cv;
+            cv.d = T.rec[((size_t)T.rec_off[g] + blk) * 8 + local];
+            const int axis = (int)(cv.b & 3ull);
             const double qa = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
-            const double diff = qa - sv;
+            const double diff = qa - cv.d;
             const uint32_t right = diff > 0.0 ? 1u : 0u;
-            if (fabs(diff) <= margin) stack[sp++] = ((uint32_t)(d + 1) << 26) | (2u * i + (1u - right));
+            if (fabs(diff) <= prune_rec) stack[sp++] = ((uint32_t)(d + 1) << 26) | (2u * i + (1u - right));
             i = 2u * i + right;
             d++;
         }
