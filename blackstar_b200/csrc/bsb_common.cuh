@@ -21,12 +21,14 @@ namespace bsb {
 //   K = cos(a)/cos(b) of the sector (oracle/oracle_thirdparty.c),
 // so the two cosines and the division are paid once per star at upload, not once per hit.
 // kr/kg/kb hold  sat_star * k_c ; the frame's starSaturation multiplies them in the kernel.
+// (fx, fy, fz) is the position rounded to float: a leaf slot is rejected with six FP32
+// operations unless it is within radius + 1e-6 of the query, and only then tested exactly.
 struct StarRec {
     double x, y, z;
     double kr, kg, kb;
+    // one 16-byte word for the leaf scan's single-precision pre-filter: magnitude + float position
     int32_t mag;
-    int32_t pad0;
-    double pad1;
+    float fx, fy, fz;
 };
 static_assert(sizeof(StarRec) == 64, "StarRec is 64 bytes");
 

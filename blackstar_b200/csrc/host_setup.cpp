@@ -161,7 +161,8 @@ struct Builder {
                 const bsb_star &st = s[idx[k]];
                 double k3[3];
                 hue_coefficients(st.hue, k3);
-                slot[k - lo] = StarRec{ st.pos[0], st.pos[1], st.pos[2], st.sat * k3[0], st.sat * k3[1], st.sat * k3[2], st.mag, 0, 0.0 };
+                slot[k - lo] = StarRec{ st.pos[0], st.pos[1], st.pos[2], st.sat * k3[0], st.sat * k3[1], st.sat * k3[2], st.mag,
+                                        (float)st.pos[0], (float)st.pos[1], (float)st.pos[2] };
             }
             return;
         }
@@ -214,7 +215,7 @@ void build_star_tree(const bsb_star *stars, size_t n, HostStarTree &out)
     }
     out.rec.assign(n_rec * 8 + 8, 0.0);
     // padding record: far outside the unit sphere, never within the lookup radius
-    out.stars.assign((size_t(1) << depth) * kLeafSlots, StarRec{ 4.0, 4.0, 4.0, 0.0, 0.0, 0.0, 0, 0, 0.0 });
+    out.stars.assign((size_t(1) << depth) * kLeafSlots, StarRec{ 4.0, 4.0, 4.0, 0.0, 0.0, 0.0, 0, 4.0f, 4.0f, 4.0f });
     Builder b{ stars, std::vector<uint32_t>(n), &out, depth, T };
     std::iota(b.idx.begin(), b.idx.end(), 0u);
     b.rec(0, 0, 0, n);

@@ -465,6 +465,7 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const float *top, const double
     // each instead of two); the margin covers the rounding of the plane and of the query
     const float f0 = (float)n0, f1 = (float)n1, f2 = (float)n2;
     const float fmargin = (float)prune_top;
+    const float fr2 = (float)((radius + 1e-6) * (radius + 1e-6));
     uint32_t hits = 0;
     uint32_t stack[32];                           // (depth << 26) | index within the level
     int sp = 0;
@@ -510,6 +511,9 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const float *top, const double
 #pragma unroll
         for (int j = 0; j < kLeafSlots; j++) {
             const StarRec &st = leaf[j];
+            // single-precision pre-filter (conservative: radius + 1e-6), then the exact test
+            const float ex_ = st.fx - f0, ey_ = st.fy - f1, ez_ = st.fz - f2;
+            if (ex_ * ex_ + ey_ * ey_ + ez_ * ez_ > fr2) continue;
             const double dx = sub_rn(st.x, n0), dy = sub_rn(st.y, n1), dz = sub_rn(st.z, n2);
             const double d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)); // :107 qd
             if (d2 <= r2max) {
