@@ -20,13 +20,29 @@ namespace bsb {
 constexpr int kBloomThreads = 512;
 constexpr unsigned kFullMask = 0xffffffffu;
 
-// One CTA per line of `n` pixels (C = ceil(n / 512) pixels per thread, compile-time).
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256); the address must be 32-byte aligned.
+__device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st256(float4 *p, const float4 &a, const float4 &b)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
+// One CTA per PAIR of lines of `n` pixels (C = ceil(n / 512) pixels per thread, compile-time).
 //   in  : [lines][n] float4, row-major
 //   out : [n][lines] float4 (transposed)
 //   combine: out = img + strength * blur, img indexed like out.
+// Memory access is what bounds this kernel (L1TEX wavefronts, not DRAM bytes), so
+//   * a line is read COALESCED (512 B per warp request) into a conflict-free permuted
+//     shared-memory layout and only then redistributed so each thread owns C adjacent pixels;
+//   * the two lines of the pair are filtered one after the other and written together: in the
+//     transposed image they are adjacent, so each thread moves 32 contiguous bytes per pixel with
+//     one 256-bit store (and one 256-bit load of `img` in the combine launch) -- a full sector.
 // The line lives in registers as float (what the framebuffer holds anyway); every sum is FP64.
-// 48 registers and 3*C*4 KB of shared memory per CTA -> two CTAs per SM up to n = 4096, so one
-// CTA's loads/stores overlap the other's scans.
 template <int C>
 __global__ void __launch_bounds__(kBloomThreads, (C <= 8) ? 2 : 1)
 box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, const float4 *__restrict__ img,
@@ -34,98 +50,124 @@ box3_transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, c
 {
     extern __shared__ double s_mem[];
     constexpr int T = kBloomThreads;
+    constexpr int TP = T + 32 / C;      // plane pitch of the staging layout: TP = 32/C (mod 32) => conflict free
     double *P = s_mem;                  // [3][C*T] inclusive prefix sums, element x at (x % C) * T + x / C
     double *s_wt = s_mem + 3 * C * T;   // [3][16] warp totals
+    float *S = reinterpret_cast<float *>(s_mem);  // staging [3][C*TP] floats, aliases P (dead at that time)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int line = blockIdx.x;
+    const int line0 = 2 * blockIdx.x;
+    const int n_here = (line0 + 1 < lines) ? 2 : 1;
 
-    float v[C][3];
+    float res[2][C][3];
 #pragma unroll
-    for (int j = 0; j < C; j++) {
-        const int x = t * C + j;
-        if (x < n) {
-            const float4 p = __ldg(&in[(size_t)line * n + x]);
-            v[j][0] = p.x; v[j][1] = p.y; v[j][2] = p.z;
-        } else {
-            v[j][0] = v[j][1] = v[j][2] = 0.0f;
-        }
-    }
-
-#pragma unroll 1
-    for (int pass = 0; pass < 3; pass++) {
-        // block-wide exclusive offset of this thread's chunk, per channel
-        double excl[3];
+    for (int half = 0; half < 2; half++) {
+        float v[C][3] = {};
+        if (half < n_here) {
+            // coalesced read: consecutive threads read consecutive pixels; element x goes to
+            // plane offset (x % C) * TP + x / C, which is bank-conflict free for this pattern
+            const float4 *src = in + (size_t)(line0 + half) * n;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            double tot = 0.0;
-#pragma unroll
-            for (int j = 0; j < C; j++) tot += (double)v[j][c];
-            double x = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double y = __shfl_up_sync(kFullMask, x, o);
-                if (lane >= o) x += y;
+            for (int i = 0; i < C; i++) {
+                const int x = i * T + t;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (x < n) p = __ldg(&src[x]);
+                const int o = (x % C) * TP + x / C;
+                S[o] = p.x; S[C * TP + o] = p.y; S[2 * C * TP + o] = p.z;
             }
-            excl[c] = x - tot;                       // exclusive within the warp
-            if (lane == 31) s_wt[c * 16 + warp] = x;
-        }
-        __syncthreads();
-        if (warp == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                double x = lane < 16 ? s_wt[c * 16 + lane] : 0.0;
-#pragma unroll
-                for (int o = 1; o < 16; o <<= 1) {
-                    const double y = __shfl_up_sync(kFullMask, x, o);
-                    if (lane >= o) x += y;
-                }
-                if (lane < 16) s_wt[c * 16 + lane] = x;  // inclusive over warps
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            double a = excl[c] + (warp > 0 ? s_wt[c * 16 + warp - 1] : 0.0);
+            __syncthreads();
 #pragma unroll
             for (int j = 0; j < C; j++) {
-                a += (double)v[j][c];
-                P[c * C * T + j * T + t] = a;
+                v[j][0] = S[j * TP + t]; v[j][1] = S[C * TP + j * TP + t]; v[j][2] = S[2 * C * TP + j * TP + t];
+            }
+            __syncthreads();
+
+#pragma unroll 1
+            for (int pass = 0; pass < 3; pass++) {
+                // block-wide exclusive offset of this thread's chunk, per channel
+                double excl[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int j = 0; j < C; j++) tot += (double)v[j][c];
+                    double x = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double y = __shfl_up_sync(kFullMask, x, o);
+                        if (lane >= o) x += y;
+                    }
+                    excl[c] = x - tot;                       // exclusive within the warp
+                    if (lane == 31) s_wt[c * 16 + warp] = x;
+                }
+                __syncthreads();
+                if (warp == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        double x = lane < 16 ? s_wt[c * 16 + lane] : 0.0;
+#pragma unroll
+                        for (int o = 1; o < 16; o <<= 1) {
+                            const double y = __shfl_up_sync(kFullMask, x, o);
+                            if (lane >= o) x += y;
+                        }
+                        if (lane < 16) s_wt[c * 16 + lane] = x;  // inclusive over warps
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double a = excl[c] + (warp > 0 ? s_wt[c * 16 + warp - 1] : 0.0);
+#pragma unroll
+                    for (int j = 0; j < C; j++) {
+                        a += (double)v[j][c];
+                        P[c * C * T + j * T + t] = a;
+                    }
+                }
+                __syncthreads();
+                // window [x-r+1, x+r] clipped to the line; everything outside reads as zero (:41-46)
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const int x = t * C + j;
+                    int hi = x + r;
+                    if (hi > n - 1) hi = n - 1;
+                    const int lo = x - r;
+                    const int hi_i = (hi % C) * T + hi / C;
+                    const int lo_i = lo >= 0 ? (lo % C) * T + lo / C : 0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double a = P[c * C * T + hi_i];
+                        const double b = lo >= 0 ? P[c * C * T + lo_i] : 0.0;
+                        v[j][c] = x < n ? (float)(norm * (a - b)) : 0.0f;
+                    }
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
-        // window [x-r+1, x+r] clipped to the line; everything outside reads as zero (:41-46)
 #pragma unroll
         for (int j = 0; j < C; j++) {
-            const int x = t * C + j;
-            int hi = x + r;
-            if (hi > n - 1) hi = n - 1;
-            const int lo = x - r;
-            const int hi_i = (hi % C) * T + hi / C;
-            const int lo_i = lo >= 0 ? (lo % C) * T + lo / C : 0;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const double a = P[c * C * T + hi_i];
-                const double b = lo >= 0 ? P[c * C * T + lo_i] : 0.0;
-                v[j][c] = x < n ? (float)(norm * (a - b)) : 0.0f;
-            }
+            res[half][j][0] = v[j][0]; res[half][j][1] = v[j][1]; res[half][j][2] = v[j][2];
         }
-        __syncthreads();
     }
 
+    // 32-byte aligned pairs: even line count and 32-byte aligned buffers
+    const bool wide = n_here == 2 && (lines & 1) == 0 && ((reinterpret_cast<size_t>(out) | reinterpret_cast<size_t>(img)) & 31) == 0;
 #pragma unroll
     for (int j = 0; j < C; j++) {
         const int x = t * C + j;
-        if (x < n) {
-            const size_t o = (size_t)x * lines + line;
-            if (combine) {
-                const float4 p = __ldg(&img[o]);
-                out[o] = make_float4((float)((double)p.x + strength * (double)v[j][0]),
-                                     (float)((double)p.y + strength * (double)v[j][1]),
-                                     (float)((double)p.z + strength * (double)v[j][2]), p.w);
-            } else {
-                out[o] = make_float4(v[j][0], v[j][1], v[j][2], 1.0f);
-            }
+        if (x >= n) continue;
+        const size_t o = (size_t)x * lines + line0;
+        float4 a = make_float4(res[0][j][0], res[0][j][1], res[0][j][2], 1.0f);
+        float4 b = make_float4(res[1][j][0], res[1][j][1], res[1][j][2], 1.0f);
+        if (combine) {
+            float4 pa, pb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wide) ld256(&img[o], pa, pb);
+            else { pa = __ldg(&img[o]); if (n_here == 2) pb = __ldg(&img[o + 1]); }
+            a = make_float4((float)((double)pa.x + strength * (double)a.x), (float)((double)pa.y + strength * (double)a.y),
+                            (float)((double)pa.z + strength * (double)a.z), pa.w);
+            b = make_float4((float)((double)pb.x + strength * (double)b.x), (float)((double)pb.y + strength * (double)b.y),
+                            (float)((double)pb.z + strength * (double)b.z), pb.w);
         }
+        if (wide) st256(&out[o], a, b);
+        else { out[o] = a; if (n_here == 2) out[o + 1] = b; }
     }
 }
 
@@ -134,11 +176,12 @@ static cudaError_t launch_box3_c(const float4 *in, float4 *out, const float4 *im
                                  double strength, bool combine, cudaStream_t stream)
 {
     const size_t smem = (size_t)(3 * C * kBloomThreads + 3 * 16) * sizeof(double);
+    static_assert(3 * C * (kBloomThreads + 32 / C) * sizeof(float) <= 3 * C * kBloomThreads * sizeof(double), "staging must fit in P");
     auto kern = box3_transpose_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const double norm = 1.0 / (2.0 * (double)r + 1.0);  // src/ImageFilters.hs:51
-    kern<<<lines, kBloomThreads, smem, stream>>>(in, out, img, n, lines, r, norm, strength, combine ? 1 : 0);
+    kern<<<(lines + 1) / 2, kBloomThreads, smem, stream>>>(in, out, img, n, lines, r, norm, strength, combine ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -128,7 +128,8 @@ def test_ppm_ingestion_equals_flat_list(rnd, scenes_dir):
 
 @pytest.mark.parametrize("shape,divider", [((40, 64), 25), ((64, 40), 7), ((300, 500), 25), ((270, 480), 3),
                                            ((90, 1300), 25), ((1100, 70), 2), ((33, 2500), 25), ((17, 4100), 25),
-                                           ((4100, 26), 25)])
+                                           ((4100, 26), 25), ((37, 53), 5), ((1, 30), 3), ((30, 1), 1),
+                                           ((255, 1023), 9), ((512, 2048), 25)])
 def test_bloom_vs_oracle(rnd, shape, divider):
     rng = np.random.default_rng(shape[0] * 7 + shape[1])
     H, W = shape
@@ -140,6 +141,32 @@ def test_bloom_vs_oracle(rnd, shape, divider):
     ref = po.bloom(0.4, divider, rgb(img))
     assert np.abs(rgb(got) - ref).max() < 1e-5
     assert (got[..., 3] == 1).all()
+
+
+def test_bloom_device_in_place_and_unaligned_views(rnd):
+    # the device entry point on torch tensors: in place, out of place, and on a view whose base
+    # address is only 16-byte aligned (the 256-bit path must not be taken there)
+    import torch
+    rng = np.random.default_rng(9)
+    H, W = 96, 200
+    img = np.ones((H, W, 4), dtype=np.float32)
+    img[..., :3] = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    ref = po.bloom(0.3, 10, rgb(img))
+    rnd.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        a = torch.from_numpy(img).cuda()
+        b = torch.empty_like(a)
+        rnd.bloom_device(0.3, 10, W, H, a.data_ptr(), b.data_ptr())
+        rnd.bloom_device(0.3, 10, W, H, a.data_ptr(), a.data_ptr())
+        big = torch.zeros(H * W * 4 + 4, dtype=torch.float32, device="cuda")
+        view = big[4:]                                 # +16 bytes
+        view.copy_(torch.from_numpy(img).cuda().reshape(-1))
+        rnd.bloom_device(0.3, 10, W, H, view.data_ptr(), view.data_ptr())
+        torch.cuda.synchronize()
+        for got in (b.cpu().numpy(), a.cpu().numpy(), view.cpu().numpy().reshape(H, W, 4)):
+            assert np.abs(got[..., :3].astype(np.float64) - ref).max() < 1e-5
+    finally:
+        rnd.set_stream(None)
 
 
 def test_bloom_error_behaviour(rnd):
