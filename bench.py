@@ -32,8 +32,8 @@ if ROOT not in sys.path:
 SCENE = "default-aa.yaml"
 RES = (4096, 4096)
 FLOPS_PER_STEP = 156  # 141 (rk4 as written) + 15 (findColor), sqrt/div = 1 flop
-DP_INSTR_PER_STEP = 62.1  # FP64-pipe instructions the kernel issues per RK4 step (ncu, incl. ray setup)
-OTHER_INSTR_PER_STEP = 19.7  # all other instructions per RK4 step (ncu)
+DP_INSTR_PER_STEP = 61.4  # FP64-pipe instructions the kernel issues per RK4 step (ncu, incl. ray setup)
+OTHER_INSTR_PER_STEP = 19.1  # all other instructions per RK4 step (ncu)
 METRIC = "Mrays/sec on default.yaml at 4096x4096"
 
 
@@ -399,7 +399,7 @@ def run_b200(args):
                               "executed": {"dp_instr_per_rk4_step": DP_INSTR_PER_STEP,
                                            "pipe_frac": (DP_INSTR_PER_STEP * my_steps / (k1_ms * 1e-3)) / (fp64_peak * 1e12 / 2)
                                            if fp64_peak else None,
-                                           "note": "the kernel executes 62.1 FP64 (+19.7 other) instructions per RK4 step (ncu, "
+                                           "note": "the kernel executes 61.4 FP64 (+19.1 other) instructions per RK4 step (ncu, "
                                                    "profiles/r01_ncu_summary.json) where the reference as written "
                                                    "needs 156 flops, so the algorithmic frac can exceed 1; pipe_frac "
                                                    "is executed FP64 instructions / DFMA issue peak; an FP64 "
