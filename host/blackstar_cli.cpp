@@ -20,6 +20,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -181,8 +185,63 @@ bool prompt_overwrite(const std::string &path)
     return !ans.empty() && (ans[0] == 'y' || ans[0] == 'Y');
 }
 
+// Batch mode (app/Main.hs:64-77) renders the scenes strictly one after the other; here the PNG of
+// scene k is deflated and written by a background thread while the GPU traces scene k+1 (row N4 of
+// SURVEY.md section 8f).  Only with --force: the overwrite prompt needs the terminal.
+class PngWriter {
+public:
+    explicit PngWriter(bool background) : background_(background)
+    {
+        if (background_) th_ = std::thread([this] { run(); });
+    }
+    ~PngWriter() { finish(); }
+    void submit(std::string path, std::vector<uint8_t> rgb, int w, int h)
+    {
+        if (!background_) { write(path, rgb, w, h); return; }
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return q_.size() < 2; });   // at most two frames in flight
+        q_.push_back(Job{ std::move(path), std::move(rgb), w, h });
+        cv_.notify_all();
+    }
+    void finish()
+    {
+        if (!background_ || !th_.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m_); done_ = true; }
+        cv_.notify_all();
+        th_.join();
+    }
+
+private:
+    struct Job { std::string path; std::vector<uint8_t> rgb; int w, h; };
+    static void write(const std::string &path, const std::vector<uint8_t> &rgb, int w, int h)
+    {
+        const std::string err = pngw::write_rgb8_parallel(path, rgb.data(), w, h);
+        if (!err.empty()) std::cout << err << std::endl;
+    }
+    void run()
+    {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = std::move(q_.front());
+                q_.pop_front();
+                cv_.notify_all();
+            }
+            write(j.path, j.rgb, j.w, j.h);
+        }
+    }
+    bool background_, done_ = false;
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+};
+
 // Main.handleScene + doRender (app/Main.hs:80-125)
-void handle_scene(bsb_ctx *ctx, const Options &o, const std::string &outdir, const std::string &filename)
+void handle_scene(bsb_ctx *ctx, const Options &o, const std::string &outdir, const std::string &filename, PngWriter &writer)
 {
     std::string name = base_name(filename);
     std::cout << "Reading " << filename << "..." << std::endl;
@@ -212,10 +271,7 @@ void handle_scene(bsb_ctx *ctx, const Options &o, const std::string &outdir, con
                 (unsigned long long)st.rays, st.trace_ms > 0 ? st.rays / st.trace_ms / 1e3 : 0.0, st.n_gpus);
     const std::string out_name = outdir + "/" + name + ".png";
     std::cout << "Saving to " << out_name << "..." << std::endl;
-    if (o.force || prompt_overwrite(out_name)) {
-        const std::string err = pngw::write_rgb8(out_name, rgb.data(), cfg.scn.width, cfg.scn.height);
-        if (!err.empty()) std::cout << err << std::endl;
-    }
+    if (o.force || prompt_overwrite(out_name)) writer.submit(out_name, std::move(rgb), cfg.scn.width, cfg.scn.height);
     std::cout << "Everything done. Thank you!" << std::endl;
 }
 
@@ -270,6 +326,24 @@ int main(int argc, char **argv)
             const std::string err = pngw::write_rgb8(argv[++i], px.data(), w, h);
             if (!err.empty()) { std::cout << err << std::endl; return 2; }
             return 0;
+        } else if (a == "--selftest-png-parallel") {
+            // a frame large enough for several deflate bands; pixels follow a fixed formula
+            if (i + 2 >= argc) return usage(1);
+            const std::string path = argv[++i];
+            const int threads = std::atoi(argv[++i]);
+            const int w = 1031, h = 517;
+            std::vector<uint8_t> px((size_t)w * h * 3);
+            uint32_t lcg = 12345u;
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++) {
+                    lcg = lcg * 1664525u + 1013904223u;
+                    px[((size_t)y * w + x) * 3 + 0] = uint8_t((x * 3 + y) & 255);
+                    px[((size_t)y * w + x) * 3 + 1] = uint8_t((lcg >> 24) & 255);
+                    px[((size_t)y * w + x) * 3 + 2] = uint8_t(((x ^ y) * 5) & 255);
+                }
+            const std::string err = pngw::write_rgb8_parallel(path, px.data(), w, h, threads);
+            if (!err.empty()) { std::cout << err << std::endl; return 2; }
+            return 0;
         } else if (!a.empty() && a[0] == '-') { std::cerr << "Unknown flag: " << a << "\n"; return usage(1); }
         else pos.push_back(a);
     }
@@ -307,12 +381,15 @@ int main(int argc, char **argv)
             closedir(d);
         }
         std::sort(files.begin(), files.end());
+        PngWriter writer(o.force);
         for (size_t k = 0; k < files.size(); k++) {
             std::cout << "Batch mode progress: " << (k + 1) << "/" << files.size() << std::endl;
-            handle_scene(ctx, o, outdir, filename + "/" + files[k]);
+            handle_scene(ctx, o, outdir, filename + "/" + files[k], writer);
         }
+        writer.finish();
     } else {
-        handle_scene(ctx, o, outdir, filename);
+        PngWriter writer(false);
+        handle_scene(ctx, o, outdir, filename, writer);
     }
     bsb_destroy(ctx);
     return 0;

@@ -87,6 +87,27 @@ def test_png_writer(exe, tmp_path):
     np.testing.assert_array_equal(a[..., 2], (x * 7 + y * 13) & 255)
 
 
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_parallel_png_writer(exe, tmp_path, threads):
+    # pigz-style banded deflate: one zlib stream, any decoder must read it back exactly
+    from PIL import Image
+    out = str(tmp_path / "p.png")
+    assert subprocess.run([exe, "--selftest-png-parallel", out, str(threads)]).returncode == 0
+    a = np.array(Image.open(out))
+    w, h = 1031, 517
+    assert a.shape == (h, w, 3)
+    y, x = np.mgrid[0:h, 0:w]
+    np.testing.assert_array_equal(a[..., 0], (x * 3 + y) & 255)
+    np.testing.assert_array_equal(a[..., 2], ((x ^ y) * 5) & 255)
+    lcg = np.uint32(12345)
+    g = np.empty(w * h, dtype=np.uint8)
+    state = 12345
+    for k in range(w * h):
+        state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+        g[k] = state >> 24
+    np.testing.assert_array_equal(a[..., 1].reshape(-1), g)
+
+
 def test_refuses_to_start_without_star_map(exe, scenes_dir):
     # app/Main.hs:46-50
     r = subprocess.run([exe, "-s", "/no/such/stars", os.path.join(scenes_dir, "default.yaml")], capture_output=True, text=True)
