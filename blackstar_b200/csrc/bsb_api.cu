@@ -348,7 +348,7 @@ extern "C" int bsb_set_option(bsb_ctx *ctx, const char *key, double value)
 {
     if (!ctx || !key) return BSB_ERR_INVALID;
     if (std::strcmp(key, "trace_variant") == 0) {
-        if (value < 0 || value > 6) return fail(ctx, BSB_ERR_INVALID, "trace_variant must be 0..6");
+        if (value < 0 || value > 6 || (int)value == 5) return fail(ctx, BSB_ERR_INVALID, "trace_variant must be 0..4 or 6");
         ctx->trace_variant = (int)value;
         return BSB_OK;
     }

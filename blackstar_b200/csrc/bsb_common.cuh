@@ -97,8 +97,7 @@ struct FrameParams {
     int32_t row0, row1;       // final-image rows rendered by this launch
     int32_t tiles_x, tiles_y, n_tiles;
     uint32_t step_cap;        // the reference has no cap (Raytracer.hs:80-85); ours is a safety net
-    uint32_t stagger_unit;    // cycles between the start times of an SM sub-partition's warps (0 = off)
-    int32_t n_sms;
+    uint32_t pad1_;
 };
 
 // Per-launch counters (device memory, zeroed before the launch).

@@ -121,8 +121,6 @@ std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int r
     }
     P.n_tiles = P.tiles_x * P.tiles_y;
     P.step_cap = 1000000u;
-    P.stagger_unit = 0;
-    P.n_sms = 0;
     return "";
 }
 

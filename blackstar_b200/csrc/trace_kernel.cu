@@ -103,15 +103,6 @@ trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ o
 
     const int lane = threadIdx.x & 31;
     unsigned long long my_steps = 0, my_capped = 0, my_hits = 0;
-    if (P.stagger_unit != 0u) {
-        // Tiles take almost identical time (step counts are flat), so warps that start together
-        // stay in lockstep and reach the FP64-idle phases (ray setup, sky lookup) together.
-        // Offset the k-th warp of each SM sub-partition by k/8 of a tile time, once.
-        const int slot = P.n_sms > 0 ? (int)(blockIdx.x / (unsigned)P.n_sms) : 0;
-        const long long delay = (long long)P.stagger_unit * (long long)(((threadIdx.x >> 7) + 2 * slot) & 7);
-        const long long t0 = clock64();
-        while (clock64() - t0 < delay) __nanosleep(2000);
-    }
     for (;;) {
         unsigned tile = 0;
         if (lane == 0) tile = atomicAdd(&ctr->next_tile, 1u);
@@ -317,22 +308,13 @@ static int persistent_grid(K kernel, int n_sms)
 }
 
 // variant: 0 = tiles, 1 = refill(block 16, min 8 lanes), 2 = refill(block 8, min 4), 3 = refill(block 32, min 8),
-//          4 = tiles compiled for 4 CTAs/SM (64 registers), 5 = 4 + staggered warp start,
-//          6 = tiles compiled for 2 CTAs/SM (<= 128 registers: every loop constant stays in a register)
+//          4 = tiles compiled for 4 CTAs/SM (64 registers),
+//          6 = tiles compiled for 2 CTAs/SM (<= 128 registers: every loop constant stays in a register; default)
 cudaError_t launch_trace(const FrameParams &P_in, float4 *out, TraceCounters *ctr, int n_sms, int variant,
                          cudaStream_t stream)
 {
     if (P_in.n_tiles <= 0) return cudaSuccess;
-    FrameParams P = P_in;
-    P.n_sms = n_sms;
-    if (variant == 5) {
-        // ~ (path length / step) RK4 steps per ray x ~136 cycles of FP64 pipe per warp-step
-        const double steps = (P.r0 + sqrt(P.safe2)) / P.h;
-        const double unit = steps * 136.0;
-        P.stagger_unit = unit > 4.0e6 ? 4000000u : (unsigned)unit;
-        if ((long long)P.n_tiles < 16LL * n_sms * 32) P.stagger_unit = 0;  // tiny launches: not worth it
-        variant = 4;
-    }
+    const FrameParams &P = P_in;
 #define BSB_LAUNCH(KERNEL)                                                                        \
     do {                                                                                          \
         int grid = persistent_grid(KERNEL, n_sms);                                                \

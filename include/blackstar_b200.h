@@ -106,8 +106,11 @@ const char *bsb_version(void);
  * NULL restores the ctx's stream; pass cudaStreamLegacy ((void*)1) for the default stream. */
 int bsb_set_stream(bsb_ctx *ctx, void *cuda_stream);
 
-/* Tuning knobs.  "trace_variant": 0 = one tile of 32 rays per warp, 1..3 = persistent warps
- * with ballot compaction (step block 16/8/32).  Same arithmetic, same image. */
+/* Tuning knobs.  "trace_variant" selects the schedule / build of the trace kernel; every variant
+ * computes the same image bit for bit:
+ *   6 (default) one tile of 32 rays per warp, <=128 registers (2 CTAs/SM)
+ *   0 / 4       same schedule compiled for 3 / 4 CTAs per SM (80 / 64 registers)
+ *   1 / 2 / 3   persistent warps with ballot compaction of live rays between blocks of 16 / 8 / 32 steps */
 int bsb_set_option(bsb_ctx *ctx, const char *key, double value);
 
 /* ---- star map: replaces StarMap.readTreeFromFile + the StarTree argument --------------
