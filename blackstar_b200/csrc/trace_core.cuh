@@ -219,12 +219,15 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
     F.iL = iL;
     F.qh = iL2;
     const double s2 = n0 * n0 + n2 * n2;
-    if (!(h2 > 1e-280) || !(s2 > 1e-28 * h2)) {
+    // h2 below ~1e-24 |cam|^2 is rounding noise of the cross product (the ray points at the hole to
+    // within 1e-12 rad): n is then meaningless as a plane normal, and the motion is a line anyway.
+    const bool radial = !(h2 > 1e-24 * P.q0);
+    if (radial || !(s2 > 1e-28 * h2)) {
         // radial ray (no plane) or a plane that IS the disk plane: f1 = cam/|cam|, f2 any
         // in-plane unit vector orthogonal to it.
         F.f1[0] = P.e1[0]; F.f1[1] = P.e1[1]; F.f1[2] = P.e1[2];
         double w0, w1, w2;
-        if (h2 > 1e-280) {  // f2 = nhat x f1
+        if (!radial) {  // f2 = nhat x f1
             const double in = 1.0 / sqrt(h2);
             w0 = (n1 * P.e1[2] - n2 * P.e1[1]) * in;
             w1 = (n2 * P.e1[0] - n0 * P.e1[2]) * in;
@@ -238,7 +241,7 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
         }
         const double iw = 1.0 / sqrt(w0 * w0 + w1 * w1 + w2 * w2);
         F.f2[0] = w0 * iw; F.f2[1] = w1 * iw; F.f2[2] = w2 * iw;
-        F.ysign = (h2 > 1e-280) ? 0 : ((P.e1[1] > 0.0) - (P.e1[1] < 0.0));
+        F.ysign = !radial ? 0 : ((P.e1[1] > 0.0) - (P.e1[1] < 0.0));
         return;
     }
     // general case: f2 along the line of nodes (n x yhat), f1 = nhat x f2; then f1y = -s/|n| < 0

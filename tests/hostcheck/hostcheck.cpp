@@ -90,6 +90,23 @@ void hc_star_lookup(void *p, double intensity, double saturation, const double v
     *hits = star_lookup(P, P.tree.top, vel, rgb);
 }
 
+// one ray of the traced grid (gx, gy): colour, RK4 steps taken, final status
+int hc_trace_ray(void *p, const bsb_camera *cam, const bsb_scene *scn, int gx, int gy, double rgb[3], unsigned *steps, int *status)
+{
+    HcCtx *c = static_cast<HcCtx *>(p);
+    FrameParams P;
+    if (!make_frame_params(*cam, *scn, 0, scn->height, P).empty()) return 1;
+    attach(c, P);
+    RayState s;
+    RayFrame F;
+    ray_init(P, gx, gy, s, F);
+    ray_advance(P, s, 0xffffffffu);
+    ray_finish(P, P.tree.top, F, s, rgb);
+    *steps = s.steps;
+    *status = s.status;
+    return 0;
+}
+
 double hc_rinv5(double q) { double yh = 0.0; return rinv5(q, yh, 4.375); }
 
 }  // extern "C"

@@ -309,3 +309,23 @@ def test_animation_frame_1080p_supersampled(rnd, scenes_dir):
     assert np.abs(rgb(img[500:503]) - ref).max() < TOL
     full = rnd.do_render(cfg)
     assert np.isfinite(full).all() and (rgb(full) >= rgb(img) - 1e-6).all()
+
+
+@pytest.mark.parametrize("seed", [3, 19, 40, 41, 57, 77, 90])
+def test_random_scenes_match_oracle(rnd, stars40k, seed):
+    # the randomized scenes of tests/test_hostcheck.py (cameras in the disk plane, on the polar axis,
+    # looking straight at the hole ...) through the real kernels; seed 19 contains an exactly radial ray
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("th", os.path.join(HERE, "test_hostcheck.py"))
+    th = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(th)
+    cfg = th._random_config(np.random.default_rng(1000 + seed))
+    rnd.set_stars(stars40k)
+    ref, rsteps = po.render(cfg, po.Tree(stars40k))
+    nrays = ref.shape[0] * ref.shape[1] * (4 if cfg.scene.supersampling else 1)
+    for variant in (6, 1):
+        rnd.set_option("trace_variant", variant)
+        img = rnd.render(cfg)
+        assert np.abs(rgb(img) - ref).max() < TOL
+        assert rnd.last_stats["steps"] == rsteps - nrays
+    rnd.set_option("trace_variant", 6)

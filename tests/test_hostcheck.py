@@ -145,3 +145,49 @@ def test_degenerate_geometry(hc, scenes_dir, case):
         hc.hc_destroy(h_)
     assert np.abs(got - ref).max() < 1e-9
     assert steps == rsteps - ref.shape[0] * ref.shape[1]
+
+
+def _random_config(rng):
+    """A random but sane scene: camera anywhere between 2.5 and 80 radii, any orientation, random
+    disk, step size, field of view; sometimes exactly in the disk plane, on an axis, or inside the disk."""
+    r = float(np.exp(rng.uniform(np.log(2.5), np.log(80.0))))
+    d = rng.normal(0, 1, 3)
+    d /= np.linalg.norm(d)
+    pos = r * d
+    kind = rng.integers(6)
+    if kind == 0:
+        pos[1] = 0.0                      # exactly in the disk plane (signum 0 at the start)
+    elif kind == 1:
+        pos = np.array([0.0, r, 0.0])     # on the polar axis
+    look = rng.normal(0, 2.0, 3) if rng.random() < 0.7 else np.zeros(3)
+    up = rng.normal(0, 1, 3)
+    inner = float(rng.uniform(1.2, 4.0))
+    scn = config.Scene(stepSize=float(rng.choice([0.3, 0.3, 0.2, 0.45, 0.1])), bloomStrength=0.0, bloomDivider=25,
+                       starIntensity=float(rng.uniform(0.2, 1.0)), starSaturation=float(rng.uniform(0.0, 1.6)),
+                       diskColor=(float(rng.uniform(0, 0.999)), float(rng.uniform(0, 0.5)), float(rng.uniform(0.5, 1.1))),
+                       diskOpacity=float(rng.choice([0.0, 0.95, 0.5, 1.0])), diskInner=inner,
+                       diskOuter=inner + float(rng.uniform(0.5, 20.0)), resolution=(20, 14),
+                       supersampling=bool(rng.integers(2)))
+    cam = config.Camera(position=tuple(float(x) for x in pos), lookAt=tuple(float(x) for x in look),
+                        upVec=tuple(float(x) for x in up), fov=float(rng.uniform(0.3, 3.5)))
+    return config.Config(scene=scn, camera=cam)
+
+
+@pytest.mark.parametrize("seed", range(96))
+def test_random_scenes_match_oracle(hc, seed):
+    rng = np.random.default_rng(1000 + seed)
+    cfg = _random_config(rng)
+    stars = starmap.synthetic_stars(30000, seed=23)
+    ref, rsteps = po.render(cfg, po.Tree(stars))
+    h_ = hc.hc_create(stars.ctypes.data, len(stars), 8)
+    try:
+        got, steps, _ = _hc_render(hc, h_, cfg)
+        got_b, steps_b, _ = _hc_render(hc, h_, cfg, block=7)      # odd block length: resumes mid-ray
+    finally:
+        hc.hc_destroy(h_)
+    nrays = ref.shape[0] * ref.shape[1] * (4 if cfg.scene.supersampling else 1)
+    assert np.isfinite(ref).all()
+    assert np.abs(got - ref).max() < 1e-8, cfg
+    assert steps == rsteps - nrays, cfg
+    np.testing.assert_array_equal(got, got_b)
+    assert steps_b == steps
