@@ -247,11 +247,26 @@ struct Parser {
 
 }  // namespace detail
 
+// bracket depth of flow collections left open at the end of `t` (quotes respected)
+inline int flow_depth(const std::string &t, int depth)
+{
+    bool sq = false, dq = false;
+    for (char c : t) {
+        if (c == '\'' && !dq) sq = !sq;
+        else if (c == '"' && !sq) dq = !dq;
+        else if (!sq && !dq) {
+            if (c == '[' || c == '{') depth++;
+            else if (c == ']' || c == '}') depth--;
+        }
+    }
+    return depth;
+}
+
 inline NodeP parse(const std::string &text)
 {
     detail::Parser p;
     size_t pos = 0;
-    int no = 0;
+    int no = 0, open = 0;
     while (pos <= text.size()) {
         size_t e = text.find('\n', pos);
         if (e == std::string::npos) e = text.size();
@@ -262,11 +277,20 @@ inline NodeP parse(const std::string &text)
         raw = detail::strip_comment(raw);
         int ind = 0;
         while (ind < (int)raw.size() && raw[ind] == ' ') ind++;
-        if (ind < (int)raw.size() && raw[ind] == '\t') throw std::runtime_error("line " + std::to_string(no) + ": tab in indentation");
         const std::string t = detail::trim(raw);
+        if (open > 0) {
+            // continuation of a flow collection that spans lines (PyYAML wraps long ones)
+            if (!t.empty()) p.lines.back().text += " " + t;
+            open = flow_depth(t, open);
+            continue;
+        }
+        if (ind < (int)raw.size() && raw[ind] == '\t') throw std::runtime_error("line " + std::to_string(no) + ": tab in indentation");
         if (t.empty() || t == "---") continue;
         p.lines.push_back({ ind, t, no });
+        open = flow_depth(t, 0);
+        if (open < 0) open = 0;
     }
+    if (open > 0) throw std::runtime_error("unterminated flow collection at end of input");
     if (p.lines.empty()) return std::make_shared<Node>();
     NodeP root = p.block(0);
     if (p.i < p.lines.size()) p.fail(p.lines[p.i], "unexpected content");

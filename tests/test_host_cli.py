@@ -139,3 +139,36 @@ def test_cli_render_equals_python_path(exe, scenes_dir, tmp_path):
     assert sorted(f for f in os.listdir(out) if f.startswith("prev-")) == sorted(
         "prev-" + f[:-5] + ".png" for f in os.listdir(scenes_dir) if f.endswith(".yaml"))
     assert Image.open(out / "prev-default.png").size == (300, 168)
+
+
+@pytest.mark.parametrize("style", [None, False, True])
+def test_yaml_loader_fuzz_against_pyyaml(exe, tmp_path, style):
+    # random scene files written by PyYAML in block, mixed and flow style; the C++ loader must agree
+    # with the Python mirror of src/ConfigFile.hs on every one
+    import yaml
+    rng = np.random.default_rng(5 if style is None else int(style) + 6)
+    keys = ["stepSize", "bloomStrength", "bloomDivider", "starIntensity", "starSaturation", "diskColor",
+            "diskOpacity", "diskInner", "diskOuter", "resolution", "supersampling"]
+    for k in range(25):
+        scene = {}
+        for key in keys:
+            if rng.random() < 0.6:
+                if key == "bloomDivider":
+                    scene[key] = int(rng.integers(1, 60))
+                elif key == "diskColor":
+                    scene[key] = [float(rng.uniform(0, 359)), float(rng.uniform(0, 1)), float(rng.uniform(0, 1.2))]
+                elif key == "resolution":
+                    scene[key] = [int(rng.integers(1, 5000)), int(rng.integers(1, 5000))]
+                elif key == "supersampling":
+                    scene[key] = bool(rng.integers(2))
+                else:
+                    scene[key] = float(rng.choice([rng.uniform(0, 3), int(rng.integers(0, 20)), 1e-3, 2.5e2]))
+        scene["notAKey"] = [1, 2, {"deep": "x"}]
+        cam = {"position": [float(x) for x in rng.normal(0, 20, 3)], "lookAt": [int(x) for x in rng.integers(-5, 5, 3)],
+               "upVec": [float(x) for x in rng.normal(0, 1, 3)], "fov": float(rng.uniform(0.2, 4))}
+        doc = {"camera": cam, "scene": scene} if k % 2 else {"scene": scene, "camera": cam}
+        p = tmp_path / f"f{k}.yaml"
+        p.write_text(yaml.safe_dump(doc, default_flow_style=style, sort_keys=bool(k % 3)))
+        got = _dump(exe, str(p))
+        want = _as_dict(config.load_config(str(p)))
+        assert got == want, p.read_text()
