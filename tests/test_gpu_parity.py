@@ -329,3 +329,32 @@ def test_random_scenes_match_oracle(rnd, stars40k, seed):
         assert np.abs(rgb(img) - ref).max() < TOL
         assert rnd.last_stats["steps"] == rsteps - nrays
     rnd.set_option("trace_variant", 6)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_every_scene_at_native_resolution(rnd, scenes_dir, scene):
+    # every scene of scenes/ at the resolution it ships with (supersampling as configured), full
+    # 468 861-star catalogue: two bands of rows against the oracle, bloom sanity on the whole frame
+    cfg = config.load_config(f"{scenes_dir}/{scene}.yaml")
+    W, H = cfg.scene.resolution
+    stars = starmap.synthetic_stars()
+    rnd.set_stars(stars)
+    rnd.set_option("trace_variant", 6)
+    img = rnd.render(cfg)
+    assert img.shape == (H, W, 4) and np.isfinite(img).all() and rnd.last_stats["capped"] == 0
+    tree = _full_tree(stars)
+    rng = np.random.default_rng(len(scene))
+    for r0 in (int(rng.integers(0, H - 2)), H // 2):
+        ref, _ = po.render(cfg, tree, r0, r0 + 2)
+        assert np.abs(rgb(img[r0:r0 + 2]) - ref).max() < TOL
+    full = rnd.do_render(cfg)
+    assert np.isfinite(full).all() and (rgb(full) >= rgb(img) - 1e-6).all()
+
+
+_TREE_CACHE = {}
+
+
+def _full_tree(stars):
+    if "t" not in _TREE_CACHE:
+        _TREE_CACHE["t"] = po.Tree(stars)
+    return _TREE_CACHE["t"]
