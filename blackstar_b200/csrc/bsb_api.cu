@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -100,6 +101,8 @@ struct DeviceState {
     double *d_vy = nullptr;    size_t vy_cap = 0;
     double *d_misc = nullptr;                         // 2 doubles for self-tests
     cudaEvent_t ev[6] = {};
+    double rows_per_ms = 0.0;                         // measured trace rate of the previous bsb_render_full tile
+    int last_rows = 0;
 };
 
 }  // namespace
@@ -531,8 +534,25 @@ int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn
     BSB_CUDA(ctx, cudaSetDevice(d0.dev));
     int rc = ensure(ctx, d0.d_frame, d0.frame_cap, npix);
     if (rc) return rc;
+    // Row tiles.  First frame: equal shares.  Afterwards: proportional to the rate every GPU
+    // achieved on its previous tile (rows per millisecond), so that tiles with fewer RK4 steps per
+    // ray (the hole, the far sky) get more rows and all GPUs finish together.
     std::vector<int> r0(n), r1(n);
-    for (int k = 0; k < n; k++) { r0[k] = (int)((long long)H * k / n); r1[k] = (int)((long long)H * (k + 1) / n); }
+    {
+        double total_rate = 0;
+        bool known = n > 1;
+        for (int k = 0; k < n; k++) { known = known && ctx->devs[k].rows_per_ms > 0; total_rate += ctx->devs[k].rows_per_ms; }
+        double acc = 0;
+        for (int k = 0; k < n; k++) {
+            r0[k] = k == 0 ? 0 : r1[k - 1];
+            if (known) {
+                acc += ctx->devs[k].rows_per_ms / total_rate;
+                r1[k] = k == n - 1 ? H : std::max(r0[k], std::min(H, (int)(acc * H + 0.5)));
+            } else {
+                r1[k] = (int)((long long)H * (k + 1) / n);
+            }
+        }
+    }
     for (int k = 1; k < n; k++) {
         DeviceState &d = ctx->devs[k];
         BSB_CUDA(ctx, cudaSetDevice(d.dev));
@@ -545,8 +565,10 @@ int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn
         float4 *dst = k == 0 ? d0.d_frame : d.d_frame;
         rc = trace_async(ctx, d, cam, scn, r0[k], r1[k], dst, d.ev[0], d.ev[1]);
         if (rc) return rc;
+        d.last_rows = r1[k] - r0[k];
     }
-    int launches = 2 * n;  // ray tables + trace on every GPU
+    int launches = 0;  // ray tables + trace on every GPU that has rows
+    for (int k = 0; k < n; k++) launches += r1[k] > r0[k] ? 2 : 0;
     // the single collective of the path: gather the tiles on GPU 0 (grouped send/recv)
     if (n > 1) {
         int nrc = ctx->nccl.GroupStart();
@@ -585,6 +607,7 @@ int collect_full_stats(bsb_ctx *ctx, bsb_stats *st)
         float ms = 0;
         BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
         if (ms > trace_ms) trace_ms = ms;
+        d.rows_per_ms = (d.last_rows >= 8 && ms > 1e-3f) ? d.last_rows / (double)ms : 0.0;
         fill_counter_stats(d, st);
     }
     DeviceState &d0 = ctx->devs[0];
