@@ -149,7 +149,7 @@ trace_tiles_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ o
 // (U = 32 or 8 units per tile), so consecutive jobs are neighbours on the image and in
 // the star tree.
 template <bool SS, int kBlockSteps, int kRefillMin>
-__global__ void __launch_bounds__(kTraceThreads, 3)
+__global__ void __launch_bounds__(kTraceThreads, 2)
 trace_refill_kernel(const __grid_constant__ FrameParams P, float4 *__restrict__ out, TraceCounters *ctr)
 {
     __shared__ float s_top[kSmemTreeNodes + 1];

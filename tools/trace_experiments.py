@@ -19,7 +19,7 @@ variants = {
     "closeup cam (16% captured)": (config.with_resolution(config.load_config("scenes/closeup.yaml"), 4096, 3072), stars),
 }
 with Renderer(devices=[0]) as r:
-    for v in (6,):
+    for v in (6, 1, 3):
         r.set_option("trace_variant", v)
         for name, (cfg, st) in variants.items():
             r.set_stars(st)
