@@ -49,16 +49,6 @@ inline double sqrt_rn(double a) { return std::sqrt(a); }
 inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
 #endif
 
-// x^-1/2 to ~1 ulp where exact rounding is not needed (basis vectors of the orbital plane)
-BSB_HD double rsqrt_(double x)
-{
-#if defined(__CUDA_ARCH__)
-    return rsqrt(x);
-#else
-    return 1.0 / std::sqrt(x);
-#endif
-}
-
 // Seed for x^-1/2.  Device: MUFU.RSQ64H via rsqrt.approx.ftz.f64 (looks at the high word of
 // x only; ~20 good bits).  Host: an emulation with the same information loss, so hostcheck
 // exercises the correction polynomial at the accuracy the hardware seed has.
@@ -255,12 +245,12 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
         return;
     }
     // general case: f2 along the line of nodes (n x yhat), f1 = nhat x f2; then f1y = -s/|n| < 0
-    const double in = rsqrt_(h2);
+    const double in = 1.0 / sqrt(h2);
     const double nh0 = n0 * in, nh1 = n1 * in, nh2 = n2 * in;
     double g0 = -n2, g1 = 0.0, g2 = n0;
     const double dp = g0 * nh0 + g2 * nh2;                 // re-orthogonalise against nhat
     g0 -= dp * nh0; g1 -= dp * nh1; g2 -= dp * nh2;
-    const double ig = rsqrt_(g0 * g0 + g1 * g1 + g2 * g2);
+    const double ig = 1.0 / sqrt(g0 * g0 + g1 * g1 + g2 * g2);
     g0 *= ig; g1 *= ig; g2 *= ig;
     F.f2[0] = g0; F.f2[1] = g1; F.f2[2] = g2;
     F.f1[0] = nh1 * g2 - nh2 * g1;
@@ -406,22 +396,21 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
         }
         if (remaining == 0) break;
         bool newest_is_b;
-        if (first_is_zero || remaining == 1) {
-            // rare: the camera sits in the disk plane (:96), or a single step is left in the budget
-            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);
+        if (first_is_zero) {
+            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);       // rare: the camera sits in the disk plane
             remaining--;
             newest_is_b = true;
         } else {
-            for (;;) {                                             // remaining >= 2 here
+            for (;;) {
                 rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);
-                if (((((hi32(ub) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qb) - lo_hi) >= span)) != 0) {
-                    remaining -= 1;
+                remaining--;
+                if (((((hi32(ub) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qb) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = true;
                     break;
                 }
                 rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, k4);
-                remaining -= 2;
-                if (((((hi32(ua) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qa) - lo_hi) >= span) | (remaining < 2u)) != 0) {
+                remaining--;
+                if (((((hi32(ua) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qa) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = false;
                     break;
                 }
