@@ -105,3 +105,24 @@ def test_synthetic_catalogue_is_deterministic_and_well_formed():
     assert full[28:36].hex() == starmap.synthetic_catalogue(1, seed=starmap.DEFAULT_SEED)[28:36].hex()
     with pytest.raises(ValueError):
         starmap.read_ppm(b"short")
+
+
+def test_rk4_loop_issue_cost_has_not_regressed():
+    # static check of the shipped kernel (no GPU): issue cycles per RK4 step of the fast loop,
+    # 2 per FP64 instruction + 1 per other instruction (profiles/README.md).  Measured builds:
+    # 133.5 for the default (<=128 registers), 136 / 138.5 for the 80 / 64-register builds.
+    import importlib.util
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    spec = importlib.util.spec_from_file_location("issue_cost", os.path.join(ROOT, "tools", "issue_cost.py"))
+    ic = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ic)
+    res = ic.loops()
+    assert len(res) == 6      # {SS, no SS} x {2, 3, 4 CTAs/SM}
+    default = [r for n, r in res.items() if n.endswith("ELi2EEEvNS_11FrameParamsEP6float4PNS_13TraceCountersE")]
+    assert len(default) == 2
+    for r in default:
+        assert r["fp64"] <= 122 and r["cycles_per_step"] <= 135.0, r
+    for r in res.values():
+        assert r["cycles_per_step"] <= 141.0, r
