@@ -337,6 +337,17 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = rays_per_frame / (e2e_ms * 1e-3) / 1e6
+    # (c) the image writeImg consumes: sRGB + 8 bit on the device, 3 bytes per pixel over PCIe
+    host8 = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+    frame.step_to_host_srgb8(host8)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        frame.step_to_host_srgb8(host8)
+    e1.record()
+    barrier()
+    e2e8_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e8_value = rays_per_frame / (e2e8_ms * 1e-3) / 1e6
     frame.enable_double_buffering()
     for _ in range(2):
         frame.step_to_host_pipelined(host)
@@ -384,7 +395,10 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 176, "d2h_bytes_per_step": W * H * 16,
                     "pipelined": {"value": e2e_pipe_value, "ms_per_step": e2e_pipe_ms,
-                                  "note": "same bytes; D2H of frame i overlaps the trace of frame i+1"}},
+                                  "note": "same bytes; D2H of frame i overlaps the trace of frame i+1"},
+                    "srgb8": {"value": e2e8_value, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": W * H * 3,
+                              "note": "synchronous; sRGB + 8-bit map (writeImg, src/Raytracer.hs:23-32) on the "
+                                      "device, the RGB8 image is what crosses PCIe"}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "trace (geodesic RK4 + sky lookup + 2x2 supersample)",
                          "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,

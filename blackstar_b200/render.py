@@ -176,6 +176,10 @@ class Renderer:
         self._check(self._L.bsb_to_srgb8(self._ctx, W, H, img.ctypes.data, out.ctypes.data))
         return out
 
+    def to_srgb8_device(self, W: int, H: int, src_ptr: int, dst_ptr: int):
+        """writeImg's pixel map on device memory: float4 frame -> packed RGB8 (asynchronous)."""
+        self._check(self._L.bsb_to_srgb8_device(self._ctx, W, H, ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr)))
+
     # ------------------------------------------------------------------ roofline helpers
     def measure_fp64_peak(self) -> float:
         v = ctypes.c_double()
