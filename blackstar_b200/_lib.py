@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblackstar_b200.so")
+#: the in-tree library; BLACKSTAR_B200_LIB overrides it (used by tools/ to time experimental builds)
+LIB_PATH = os.environ.get("BLACKSTAR_B200_LIB") or os.path.join(_HERE, "libblackstar_b200.so")
 
 #: every symbol include/blackstar_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [

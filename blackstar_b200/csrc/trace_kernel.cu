@@ -24,7 +24,10 @@
 
 namespace bsb {
 
-constexpr int kTraceThreads = 256;
+#ifndef BSB_TRACE_THREADS
+#define BSB_TRACE_THREADS 256
+#endif
+constexpr int kTraceThreads = BSB_TRACE_THREADS;
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ void stage_tree_top(const FrameParams &P, float *s_top)
