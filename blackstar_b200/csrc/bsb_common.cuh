@@ -74,8 +74,9 @@ struct FrameParams {
     double hh2;               // (h/2)^2
     double hhh;               // h*(h/2)
     double hsq6;              // h*h/6
-    double k4375;             // 4.375 (a polynomial coefficient kept in the constant bank so that ptxas
-                              // holds it in a register instead of re-materialising it every step)
+    double h3;                // h/3
+    double k14;               // 1.4 (the constant of the |pos|^-5 correction; an FP64 immediate carries
+                              // only a high word, so it lives in the constant bank / a register)
     // termination / disk: src/Raytracer.hs:58-65, 88-111
     double safe2, din2, dout2;
     double r_in, r_out;       // sqrt of din2, dout2 (diskColor' recomputes them per hit)

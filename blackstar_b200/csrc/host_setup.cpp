@@ -91,7 +91,8 @@ std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int r
     P.hh2 = (h / 2) * (h / 2);
     P.hhh = h * (h / 2);
     P.hsq6 = h * h / 6;
-    P.k4375 = 4.375;
+    P.h3 = h / 3;
+    P.k14 = 1.4;
     // src/Raytracer.hs:59-62
     const double twoq = 2 * P.q0;
     P.safe2 = 2500.0 > twoq ? 2500.0 : twoq;

@@ -8,7 +8,7 @@
 // Reference semantics: src/Raytracer.hs:34-134, src/StarMap.hs:93-115.
 //
 // B200-first restructuring.  The kernel is bound by FP64 issue, so the
-// work per RK4 step is cut from the reference's 141 flops (4 sqrt + 4 div) to 64 DP
+// work per RK4 step is cut from the reference's 141 flops (4 sqrt + 4 div) to 51 DP
 // instructions + 4 MUFU without changing the discrete map:
 //  * every ray's motion is planar (the force is central) and classical RK4 commutes with
 //    linear changes of variables, so the 6-double state (vel, pos) is integrated as 4 doubles
@@ -17,11 +17,13 @@
 //    error); only rounding (1e-16 per step) differs.
 //  * f2 is chosen horizontal, so scene-y = f1y * u: the disk-crossing test (signum y' /=
 //    signum y) is a sign-bit comparison of u, no FP64 work;
-//  * lengths are divided by L = (1.5 h2)^(1/5) per ray, which makes the force constant -1
-//    (one multiply less per force evaluation);
-//  * |pos|^-5 comes from one MUFU.RSQ64H seed and a second-order correction in 7 DP
-//    instructions instead of sqrt, three multiplies and a divide;
-//  * the stage velocities are eliminated algebraically (p3 = p2 + (h/2)^2 a1, ...);
+//  * lengths are divided by L = (3.75 h2)^(1/5) per ray, which makes the force constant -0.4:
+//    exactly the factor the |pos|^-5 primitive leaves out (one multiply less per force
+//    evaluation, and the correction polynomial needs one instruction instead of two);
+//  * |pos|^-5 comes from one MUFU.RSQ64H seed and a first-order correction in 5 DP
+//    instructions instead of sqrt, three multiplies and a divide (force error <= 1.4e-11);
+//  * the stage velocities are eliminated algebraically (p3 = p2 - (h/2)^2 a1, ...) and only a1
+//    is ever formed: the other stage accelerations enter the two weighted sums as FMAs;
 //  * horizon / escape tests compare the bit patterns of positive doubles as integers.
 #pragma once
 
@@ -87,20 +89,22 @@ BSB_HD void rsqrt_seed_into(double &y, double x)
 #endif
 }
 
-// q^(-5/2), relative error ~1e-15.  With y0 = q^-1/2 (1+d) from the seed and m = q y0^2 = 1 - e:
-//   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + O(e^3))
-//            = y0^5 (7.875 - 11.25 m + 4.375 m^2),      |e| <~ 2^-19  =>  O(e^3) <~ 5e-17.
-// 7 FP64 instructions + 1 MUFU.  `yh` is the seed holder; `k4` must hold 4.375 in a register
-// (an FP64 instruction takes one immediate, and only -11.25 / 7.875 fit as immediates there).
-BSB_HD double rinv5(double q, double &yh, double k4)
+// 0.4 q^(-5/2) (the factor 0.4 is absorbed by the ray's length scale, see ray_frame).  With
+// y0 = q^-1/2 (1+d) from the seed and e = 1 - q y0^2:
+//   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + ...) ~= 2.5 y0^5 (1.4 - q y0^2).
+// The dropped term is 4.375 e^2: |e| <= 2^-19.1 measured on the device (bsb_selftest_rinv5), so
+// the force is low by at most 1.4e-11 relative -- as if h2 were 1.4e-11 smaller, i.e. a deflection
+// error of ~1e-11 rad against the ~1e-7 rad that the 1e-4 parity bar on the star Gaussians
+// allows.  5 FP64 instructions + 1 MUFU.  `k14` must hold 1.4 in a register / the
+// constant bank: an FP64 immediate carries only the high word.
+BSB_HD double rinv5(double q, double &yh, double k14)
 {
     rsqrt_seed_into(yh, q);
     const double y0 = yh;
-    const double y2 = y0 * y0;
-    const double m = q * y2;
-    const double y4 = y2 * y2;
-    const double y5 = y4 * y0;
-    const double c = fma_(fma_(k4, m, -11.25), m, 7.875);
+    const double s = y0 * y0;
+    const double c = fma_(-q, s, k14);
+    const double s2 = s * s;
+    const double y5 = s2 * y0;
     return y5 * c;
 }
 
@@ -176,8 +180,8 @@ BSB_HD double inv_fifth_root(double a)
 
 // State of one ray between step blocks.  Coordinates are in the ray's own orbital plane,
 // basis (f1, f2) with f2 HORIZONTAL (so scene-y = f1y * u and a disk-plane crossing is a sign
-// change of u), and divided by L = (1.5 h2)^(1/5) so that the equation of motion is
-// p'' = -p / |p|^5 for every ray (classical RK4 commutes with this linear change of
+// change of u), and divided by L = (3.75 h2)^(1/5) so that the equation of motion is
+// p'' = -0.4 p / |p|^5 for every ray (classical RK4 commutes with this linear change of
 // variables, so it is still the reference's discrete map).
 struct RayState {
     double u, v;       // position / L in the (f1, f2) basis
@@ -196,7 +200,7 @@ enum : int32_t { kAlive = 0, kBlack = 1, kSky = 2, kCapped = 3, kIdle = 4 };
 
 struct RayFrame {
     double f1[3], f2[3];
-    double L;          // length scale (1.5 h2)^(1/5)
+    double L;          // length scale (3.75 h2)^(1/5)
     double iL;         // 1 / L
     double qh;         // 1 / L^2
     int32_t ysign;
@@ -210,8 +214,9 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
     const double n1 = sub_rn(mul_rn(P.cam[2], dir[0]), mul_rn(P.cam[0], dir[2]));
     const double n2 = sub_rn(mul_rn(P.cam[0], dir[1]), mul_rn(P.cam[1], dir[0]));
     const double h2 = add_rn(add_rn(mul_rn(n0, n0), mul_rn(n1, n1)), mul_rn(n2, n2));  // :73
-    // p'' = -1.5 h2 p/|p|^5 with p = L p~ gives p~'' = -(1.5 h2 / L^5) p~/|p~|^5: L^5 = 1.5 h2
-    double l5 = 1.5 * h2;
+    // p'' = -1.5 h2 p/|p|^5 with p = L p~ gives p~'' = -(1.5 h2 / L^5) p~/|p~|^5.  rinv5 returns
+    // 0.4 |p~|^-5, so the force constant wanted is 0.4: L^5 = 1.5 h2 / 0.4 = 3.75 h2
+    double l5 = 3.75 * h2;
     if (!(l5 > 1e-30)) l5 = 1e-30;    // (near-)radial ray: the force is ~1e-30 of anything else either way
     const double iL = inv_fifth_root(l5);
     const double iL2 = iL * iL;
@@ -335,27 +340,31 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
 }
 
 // One classical RK4 step of y' = f(y), f(vel,pos) = (-pos/|pos|^5, vel)  (src/Raytracer.hs:113-134)
-// from (u, v, du, dv) with q = u^2 + v^2 to (nu, nv, du, dv) with nq.  60 FP64 + 4 MUFU.
+// from (u, v, du, dv) with q = u^2 + v^2 to (nu, nv, du, dv) with nq.  51 FP64 + 4 MUFU:
+//   4 x (2 for |p|^2 + 5 for g = 0.4|p|^-5) + 23 for the stage positions and the two sums
+//   pos' = pos + h vel - h^2/6 (a1 + a2 + a3),   vel' = vel - h/6 (a1 + 2 a2 + 2 a3 + a4),
+// with a_i = g_i p_i (MINUS the acceleration).  Only a1 is formed explicitly; a2, a3, a4 enter as
+// fused multiply-adds:  S = a1 + g2 p2 + g3 p3,  D = g4 p4 - a1,  vel' = vel - h/6 D - h/3 S.
+// The stage velocities are eliminated (p3 = p2 - (h/2)^2 a1, p4 = pe - h (h/2) g2 p2).
 BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double &du, double &dv,
-                     double &nu, double &nv, double &nq, double &yh, double k4)
+                     double &nu, double &nv, double &nq, double &yh, double &yh2, double k14)
 {
-    const double g1 = rinv5(q, yh, k4);
-    const double a1u = g1 * u, a1v = g1 * v;                   // a_i hold MINUS the acceleration
+    const double g1 = rinv5(q, yh, k14);
+    const double a1u = g1 * u, a1v = g1 * v;
     const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
-    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v), yh, k4);
-    const double a2u = g2 * p2u, a2v = g2 * p2v;
+    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v), yh2, k14);
     const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
-    const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v), yh, k4);
-    const double a3u = g3 * p3u, a3v = g3 * p3v;
+    const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v), yh, k14);
     const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
-    const double p4u = fma_(-P.hhh, a2u, peu), p4v = fma_(-P.hhh, a2v, pev);
-    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v), yh, k4);
-    const double a4u = g4 * p4u, a4v = g4 * p4v;
-    const double s23u = a2u + a3u, s23v = a2v + a3v;
-    nu = fma_(-P.hsq6, a1u + s23u, peu);
-    nv = fma_(-P.hsq6, a1v + s23v, pev);
-    du = fma_(-P.h6, fma_(2.0, s23u, a1u) + a4u, du);
-    dv = fma_(-P.h6, fma_(2.0, s23v, a1v) + a4v, dv);
+    const double c2 = P.hhh * g2;
+    const double p4u = fma_(-c2, p2u, peu), p4v = fma_(-c2, p2v, pev);
+    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v), yh2, k14);
+    const double su = fma_(g3, p3u, fma_(g2, p2u, a1u)), sv = fma_(g3, p3v, fma_(g2, p2v, a1v));
+    const double du4 = fma_(g4, p4u, -a1u), dv4 = fma_(g4, p4v, -a1v);
+    nu = fma_(-P.hsq6, su, peu);
+    nv = fma_(-P.hsq6, sv, pev);
+    du = fma_(-P.h3, su, fma_(-P.h6, du4, du));
+    dv = fma_(-P.h3, sv, fma_(-P.h6, dv4, dv));
     nq = fma_(nu, nu, nv * nv);
 }
 
@@ -371,8 +380,8 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
     double ua = s.u, va = s.v, qa = s.q, du = s.du, dv = s.dv;
     double ub = ua, vb = va, qb = qa;
-    double yh = 0.0;                                            // seed holder: low word stays 0
-    const double k4 = P.k4375;
+    double yh = 0.0, yh2 = 0.0;                                 // seed holders: low words stay 0
+    const double k14 = P.k14;
     // q > 0, so doubles order like their bit patterns.  Fast test on the high words: strictly
     // between the two thresholds' high words => neither the horizon nor the escape test fires.
     const long long qh = dbits(s.qh), qs = dbits(s.qs);
@@ -397,18 +406,18 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
         if (remaining == 0) break;
         bool newest_is_b;
         if (first_is_zero) {
-            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);       // rare: the camera sits in the disk plane
+            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, yh2, k14);       // rare: the camera sits in the disk plane
             remaining--;
             newest_is_b = true;
         } else {
             for (;;) {
-                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k4);
+                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, yh2, k14);
                 remaining--;
                 if (((((hi32(ub) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qb) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = true;
                     break;
                 }
-                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, k4);
+                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, yh2, k14);
                 remaining--;
                 if (((((hi32(ua) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qa) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = false;
