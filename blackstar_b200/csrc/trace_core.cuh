@@ -347,18 +347,18 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
 // fused multiply-adds:  S = a1 + g2 p2 + g3 p3,  D = g4 p4 - a1,  vel' = vel - h/6 D - h/3 S.
 // The stage velocities are eliminated (p3 = p2 - (h/2)^2 a1, p4 = pe - h (h/2) g2 p2).
 BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double &du, double &dv,
-                     double &nu, double &nv, double &nq, double &yh, double &yh2, double k14)
+                     double &nu, double &nv, double &nq, double &yh, double k14)
 {
     const double g1 = rinv5(q, yh, k14);
     const double a1u = g1 * u, a1v = g1 * v;
     const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
-    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v), yh2, k14);
+    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v), yh, k14);
     const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
     const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v), yh, k14);
     const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
     const double c2 = P.hhh * g2;
     const double p4u = fma_(-c2, p2u, peu), p4v = fma_(-c2, p2v, pev);
-    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v), yh2, k14);
+    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v), yh, k14);
     const double su = fma_(g3, p3u, fma_(g2, p2u, a1u)), sv = fma_(g3, p3v, fma_(g2, p2v, a1v));
     const double du4 = fma_(g4, p4u, -a1u), dv4 = fma_(g4, p4v, -a1v);
     nu = fma_(-P.hsq6, su, peu);
@@ -380,7 +380,7 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
     double ua = s.u, va = s.v, qa = s.q, du = s.du, dv = s.dv;
     double ub = ua, vb = va, qb = qa;
-    double yh = 0.0, yh2 = 0.0;                                 // seed holders: low words stay 0
+    double yh = 0.0;                                            // seed holder: low word stays 0
     const double k14 = P.k14;
     // q > 0, so doubles order like their bit patterns.  Fast test on the high words: strictly
     // between the two thresholds' high words => neither the horizon nor the escape test fires.
@@ -406,18 +406,18 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
         if (remaining == 0) break;
         bool newest_is_b;
         if (first_is_zero) {
-            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, yh2, k14);       // rare: the camera sits in the disk plane
+            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k14);       // rare: the camera sits in the disk plane
             remaining--;
             newest_is_b = true;
         } else {
             for (;;) {
-                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, yh2, k14);
+                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k14);
                 remaining--;
                 if (((((hi32(ub) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qb) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = true;
                     break;
                 }
-                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, yh2, k14);
+                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, k14);
                 remaining--;
                 if (((((hi32(ua) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qa) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = false;
