@@ -15,7 +15,13 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,10 +33,11 @@ cudaError_t launch_trace(const FrameParams &P, float4 *out, TraceCounters *ctr, 
                          cudaStream_t stream);
 cudaError_t launch_ray_tables(const FrameParams &P, double *vx, double *vy, cudaStream_t stream);
 cudaError_t launch_rinv5_selftest(double q_lo, double q_hi, int n, double *d_out2, cudaStream_t stream);
-cudaError_t launch_box3_transpose(const float4 *in, float4 *out, const float4 *img, int n, int lines, int r,
-                                  double strength, bool combine, cudaStream_t stream);
+cudaError_t launch_box3(const BoxArgs &A, cudaStream_t stream);
+cudaError_t launch_bloom_long(const float4 *img, float4 *out, uint8_t *rgb8, const float *thr, float4 *tmp_a, float4 *tmp_b,
+                              int W, int H, int r, float strength, cudaStream_t stream);
 int bloom_max_line();
-cudaError_t launch_srgb8(const float4 *in, uint8_t *out, size_t npix, cudaStream_t stream);
+cudaError_t launch_srgb8(const float4 *in, uint8_t *out, const float *thr, size_t npix, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double *sink, int blocks, int iters, cudaStream_t stream);
 }  // namespace bsb
 
@@ -76,6 +83,65 @@ struct NcclApi {
 };
 constexpr int kNcclFloat = 7;  // ncclFloat32 in nccl.h
 
+// A few parked host threads that move staged chunks into the caller's (pageable) buffer.
+class CopyPool {
+public:
+    explicit CopyPool(int n) : n_(n)
+    {
+        for (int k = 0; k < n; k++) th_.emplace_back([this, k] { loop(k); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    void begin(std::function<void(int)> f)
+    {
+        std::lock_guard<std::mutex> g(m_);
+        job_ = std::move(f); pending_ = n_; gen_++;
+        cv_.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int k)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            std::function<void(int)> f;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                f = job_;
+            }
+            f(k);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::function<void(int)> job_;
+    unsigned long gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+constexpr int kStageSlots = 4;
+constexpr size_t kStageChunk = (size_t)8 << 20;
+
 struct DeviceState {
     int dev = -1;
     int n_sms = 0;
@@ -95,6 +161,10 @@ struct DeviceState {
     // scratch framebuffers
     float4 *d_frame = nullptr; size_t frame_cap = 0;  // this GPU's tile / the full frame on GPU 0
     float4 *d_tmp = nullptr;   size_t tmp_cap = 0;    // bloom's transposed intermediate
+    float4 *d_tmp2 = nullptr;  size_t tmp2_cap = 0;   // second scratch frame of the long-line bloom
+    float *d_thr = nullptr;                           // sRGB8 thresholds (256 floats)
+    uint8_t *h_stage = nullptr;                       // kStageSlots pinned chunks for copies into pageable memory
+    cudaEvent_t stage_ev[kStageSlots] = {};
     float4 *d_aux = nullptr;   size_t aux_cap = 0;    // staging for host-buffer bloom / srgb
     uint8_t *d_u8 = nullptr;   size_t u8_cap = 0;
     double *d_vx = nullptr;    size_t vx_cap = 0;     // per-frame ray tables
@@ -114,6 +184,9 @@ struct bsb_ctx {
     size_t n_stars = 0;
     NcclApi nccl;
     std::vector<ncclComm_t> comms;
+    std::unique_ptr<CopyPool> pool;   // created on the first copy into pageable memory
+    int copy_threads = 4;
+    uint32_t step_cap = 0;            // 0 = the default of make_frame_params
 };
 
 namespace {
@@ -188,9 +261,10 @@ int trace_async(bsb_ctx *ctx, DeviceState &d, const bsb_camera *cam, const bsb_s
     return BSB_OK;
 }
 
-// bloom on device d: src (h x w) -> dst (h x w); src may equal dst.  2 launches.
+// bloom on device d: src (h x w) -> dst (h x w) and / or its sRGB8 image; src may equal dst.
+// 2 launches (7 for lines too long for the shared-memory kernel).
 int bloom_async(bsb_ctx *ctx, DeviceState &d, double strength, int divider, int w, int h, const float4 *src,
-                float4 *dst)
+                float4 *dst, uint8_t *rgb8, int *launches = nullptr)
 {
     if (w <= 0 || h <= 0) return fail(ctx, BSB_ERR_INVALID, "bloom: image size must be positive");
     if (divider <= 0) return fail(ctx, BSB_ERR_INVALID, "bloom: bloomDivider must be positive (`div` by zero in the reference)");
@@ -198,15 +272,100 @@ int bloom_async(bsb_ctx *ctx, DeviceState &d, double strength, int divider, int 
     if (r < 1)
         return fail(ctx, BSB_ERR_INVALID,
                     "bloom: radius 0 (width < bloomDivider); the reference's boxBlur fails here (foldl1' of an empty window)");
-    if (w > bloom_max_line() || h > bloom_max_line())
-        return fail(ctx, BSB_ERR_UNSUPPORTED, "bloom: image side above 8192 does not fit the shared-memory line");
     BSB_CUDA(ctx, cudaSetDevice(d.dev));
     int rc = ensure(ctx, d.d_tmp, d.tmp_cap, (size_t)w * h);
     if (rc) return rc;
+    if (w > bloom_max_line() || h > bloom_max_line()) {
+        // the reference has no size limit: sequential running sums, one thread per line and channel
+        rc = ensure(ctx, d.d_tmp2, d.tmp2_cap, (size_t)w * h);
+        if (rc) return rc;
+        BSB_CUDA(ctx, launch_bloom_long(src, dst, rgb8, d.d_thr, d.d_tmp, d.d_tmp2, w, h, r, (float)strength, d.stream));
+        if (launches) *launches += 7;
+        return BSB_OK;
+    }
+    BoxArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.r = r;
+    A.norm = (float)(1.0 / (2.0 * (double)r + 1.0));  // src/ImageFilters.hs:51
+    A.thr = d.d_thr;
     // H^3: lines = rows of the image, written transposed (w x h)
-    BSB_CUDA(ctx, launch_box3_transpose(src, d.d_tmp, nullptr, w, h, r, 0.0, false, d.stream));
-    // V^3 on the transposed image: lines = w, n = h; transposes back and adds the original
-    BSB_CUDA(ctx, launch_box3_transpose(d.d_tmp, dst, src, h, w, r, strength, true, d.stream));
+    A.nseg = 1; A.seg_in[0] = src; A.seg_pitch[0] = (size_t)w; A.seg_start[0] = 0; A.seg_start[1] = w;
+    A.out = d.d_tmp; A.out_pitch = (size_t)h;
+    A.n = w; A.lines = h; A.x_lo = 0; A.x_hi = w;
+    BSB_CUDA(ctx, launch_box3(A, d.stream));
+    // V^3 on the transposed image: lines = w, n = h; transposes back, adds the original, maps to sRGB8
+    A.seg_in[0] = d.d_tmp; A.seg_pitch[0] = (size_t)h; A.seg_start[1] = h;
+    A.out = dst; A.out_pitch = (size_t)w; A.img = src;
+    A.rgb8 = rgb8; A.rgb8_pitch = (size_t)w * 3;
+    A.n = h; A.lines = w; A.x_lo = 0; A.x_hi = h; A.combine = 1; A.strength = (float)strength;
+    BSB_CUDA(ctx, launch_box3(A, d.stream));
+    if (launches) *launches += 2;
+    return BSB_OK;
+}
+
+// Device -> caller-owned host memory, asynchronously ordered on d.stream up to the point where the
+// bytes have left the device; returns after the last byte is in `dst` only for pageable targets.
+//  * page-locked target (cudaHostAlloc / cudaHostRegister, e.g. GHC's pinned ForeignPtr registered by
+//    the shim, or torch's pinned tensors): one cudaMemcpyAsync, the DMA engine writes it directly;
+//  * pageable target (plain malloc, what mallocForeignPtrBytes hands to the FFI): a cudaMemcpy to
+//    pageable memory is staged by the driver through one small buffer and runs at a fraction of the
+//    link rate, so the library stages it itself -- the frame is cut into 8 MB chunks that go through
+//    a ring of pinned buffers while a few parked host threads move finished chunks into the caller's
+//    buffer, so the PCIe transfer and the host copy overlap.
+int copy_to_host(bsb_ctx *ctx, DeviceState &d, void *dst, const void *src_dev, size_t bytes)
+{
+    if (bytes == 0) return BSB_OK;
+    BSB_CUDA(ctx, cudaSetDevice(d.dev));
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, dst);
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    if (pinned || bytes < kStageChunk / 4 || ctx->copy_threads <= 0) {
+        BSB_CUDA(ctx, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, d.stream));
+        return BSB_OK;
+    }
+    if (!d.h_stage) {
+        BSB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&d.h_stage), kStageSlots * kStageChunk, cudaHostAllocDefault));
+        for (auto &e : d.stage_ev) BSB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!ctx->pool || ctx->pool->size() != ctx->copy_threads) ctx->pool.reset(new CopyPool(ctx->copy_threads));
+    const int nchunks = (int)((bytes + kStageChunk - 1) / kStageChunk);
+    const int nt = ctx->pool->size();
+    std::vector<std::atomic<int>> copied(nchunks);
+    for (auto &c : copied) c.store(0, std::memory_order_relaxed);
+    std::atomic<int> enqueued{ 0 };
+    std::atomic<int> failed{ 0 };
+    uint8_t *out = static_cast<uint8_t *>(dst);
+    ctx->pool->begin([&, nt](int k) {
+        cudaSetDevice(d.dev);
+        for (int i = 0; i < nchunks; i++) {
+            while (enqueued.load(std::memory_order_acquire) <= i) {
+                if (failed.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            if (cudaEventSynchronize(d.stage_ev[i % kStageSlots]) != cudaSuccess) failed.store(1);
+            const size_t off = (size_t)i * kStageChunk;
+            const size_t len = std::min(kStageChunk, bytes - off);
+            const size_t a = len * k / nt, b = len * (k + 1) / nt;   // my slice of the chunk
+            std::memcpy(out + off + a, d.h_stage + (size_t)(i % kStageSlots) * kStageChunk + a, b - a);
+            copied[i].fetch_add(1, std::memory_order_release);
+        }
+    });
+    cudaError_t err = cudaSuccess;
+    for (int i = 0; i < nchunks && err == cudaSuccess; i++) {
+        if (i >= kStageSlots)   // the slot is free once every thread has copied its slice of chunk i - slots
+            while (copied[i - kStageSlots].load(std::memory_order_acquire) < nt) std::this_thread::yield();
+        const size_t off = (size_t)i * kStageChunk;
+        const size_t len = std::min(kStageChunk, bytes - off);
+        err = cudaMemcpyAsync(d.h_stage + (size_t)(i % kStageSlots) * kStageChunk, static_cast<const uint8_t *>(src_dev) + off, len,
+                              cudaMemcpyDeviceToHost, d.stream);
+        if (err == cudaSuccess) err = cudaEventRecord(d.stage_ev[i % kStageSlots], d.stream);
+        if (err == cudaSuccess) enqueued.store(i + 1, std::memory_order_release);
+    }
+    if (err != cudaSuccess) failed.store(1);
+    ctx->pool->wait();
+    if (err != cudaSuccess) return fail(ctx, BSB_ERR_CUDA, std::string("staged device-to-host copy: ") + cudaGetErrorString(err));
+    if (failed.load()) return fail(ctx, BSB_ERR_CUDA, "staged device-to-host copy failed");
     return BSB_OK;
 }
 
@@ -243,6 +402,8 @@ extern "C" bsb_ctx *bsb_create_on(const int *devices, int n)
     bsb_ctx *ctx = new bsb_ctx();
     const char *v = std::getenv("BSB_TRACE_VARIANT");
     if (v) ctx->trace_variant = std::atoi(v);
+    float thr[256];
+    srgb8_thresholds(thr);
     for (int k = 0; k < n; k++) {
         const int dev = devices[k];
         if (dev < 0 || dev >= count) {
@@ -272,6 +433,8 @@ extern "C" bsb_ctx *bsb_create_on(const int *devices, int n)
         ok = ok && cudaMalloc(reinterpret_cast<void **>(&d.d_ctr), sizeof(TraceCounters)) == cudaSuccess;
         ok = ok && cudaMallocHost(reinterpret_cast<void **>(&d.h_ctr), sizeof(TraceCounters)) == cudaSuccess;
         ok = ok && cudaMalloc(reinterpret_cast<void **>(&d.d_misc), 4 * sizeof(double)) == cudaSuccess;
+        ok = ok && cudaMalloc(reinterpret_cast<void **>(&d.d_thr), 256 * sizeof(float)) == cudaSuccess;
+        ok = ok && cudaMemcpy(d.d_thr, thr, sizeof thr, cudaMemcpyHostToDevice) == cudaSuccess;
         for (auto &ev : d.ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
         ctx->devs.push_back(d);
         if (!ok) {
@@ -326,6 +489,10 @@ extern "C" void bsb_destroy(bsb_ctx *ctx)
         if (d.h_ctr) cudaFreeHost(d.h_ctr);
         if (d.d_frame) cudaFree(d.d_frame);
         if (d.d_tmp) cudaFree(d.d_tmp);
+        if (d.d_tmp2) cudaFree(d.d_tmp2);
+        if (d.d_thr) cudaFree(d.d_thr);
+        if (d.h_stage) cudaFreeHost(d.h_stage);
+        for (auto &e : d.stage_ev) if (e) cudaEventDestroy(e);
         if (d.d_aux) cudaFree(d.d_aux);
         if (d.d_u8) cudaFree(d.d_u8);
         if (d.d_vx) cudaFree(d.d_vx);
@@ -440,7 +607,10 @@ extern "C" int bsb_render(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *
     if (rc) return rc;
     rc = trace_async(ctx, d, cam, scn, row0, row1, d.d_frame, d.ev[0], d.ev[1]);
     if (rc) return rc;
-    if (npix) BSB_CUDA(ctx, cudaMemcpyAsync(out_rgba, d.d_frame, npix * sizeof(float4), cudaMemcpyDeviceToHost, d.stream));
+    if (npix) {
+        rc = copy_to_host(ctx, d, out_rgba, d.d_frame, npix * sizeof(float4));
+        if (rc) return rc;
+    }
     BSB_CUDA(ctx, cudaEventRecord(d.ev[2], d.stream));
     BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
     bsb_stats st;
@@ -467,7 +637,7 @@ extern "C" int bsb_bloom_device(bsb_ctx *ctx, double strength, int divider, int 
     if (!ctx) return BSB_ERR_INVALID;
     if (!dev_in || !dev_out) return fail(ctx, BSB_ERR_INVALID, "bsb_bloom_device: NULL argument");
     return bloom_async(ctx, ctx->devs[0], strength, divider, width, height, static_cast<const float4 *>(dev_in),
-                       static_cast<float4 *>(dev_out));
+                       static_cast<float4 *>(dev_out), nullptr);
 }
 
 extern "C" int bsb_bloom(bsb_ctx *ctx, double strength, int divider, int width, int height, const float *in_rgba,
@@ -482,9 +652,10 @@ extern "C" int bsb_bloom(bsb_ctx *ctx, double strength, int divider, int width, 
     int rc = ensure(ctx, d.d_aux, d.aux_cap, npix);
     if (rc) return rc;
     BSB_CUDA(ctx, cudaMemcpyAsync(d.d_aux, in_rgba, npix * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
-    rc = bloom_async(ctx, d, strength, divider, width, height, d.d_aux, d.d_aux);
+    rc = bloom_async(ctx, d, strength, divider, width, height, d.d_aux, d.d_aux, nullptr);
     if (rc) return rc;
-    BSB_CUDA(ctx, cudaMemcpyAsync(out_rgba, d.d_aux, npix * sizeof(float4), cudaMemcpyDeviceToHost, d.stream));
+    rc = copy_to_host(ctx, d, out_rgba, d.d_aux, npix * sizeof(float4));
+    if (rc) return rc;
     BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
     return BSB_OK;
 }
@@ -496,7 +667,7 @@ extern "C" int bsb_to_srgb8_device(bsb_ctx *ctx, int width, int height, const vo
     if (width <= 0 || height <= 0 || !dev_in || !dev_out) return fail(ctx, BSB_ERR_INVALID, "bsb_to_srgb8_device: bad argument");
     DeviceState &d = ctx->devs[0];
     BSB_CUDA(ctx, cudaSetDevice(d.dev));
-    BSB_CUDA(ctx, launch_srgb8(static_cast<const float4 *>(dev_in), static_cast<uint8_t *>(dev_out), (size_t)width * height, d.stream));
+    BSB_CUDA(ctx, launch_srgb8(static_cast<const float4 *>(dev_in), static_cast<uint8_t *>(dev_out), d.d_thr, (size_t)width * height, d.stream));
     return BSB_OK;
 }
 
@@ -512,8 +683,9 @@ extern "C" int bsb_to_srgb8(bsb_ctx *ctx, int width, int height, const float *in
     rc = ensure(ctx, d.d_u8, d.u8_cap, npix * 3 + 16);
     if (rc) return rc;
     BSB_CUDA(ctx, cudaMemcpyAsync(d.d_aux, in_rgba, npix * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
-    BSB_CUDA(ctx, launch_srgb8(d.d_aux, d.d_u8, npix, d.stream));
-    BSB_CUDA(ctx, cudaMemcpyAsync(out_rgb8, d.d_u8, npix * 3, cudaMemcpyDeviceToHost, d.stream));
+    BSB_CUDA(ctx, launch_srgb8(d.d_aux, d.d_u8, d.d_thr, npix, d.stream));
+    rc = copy_to_host(ctx, d, out_rgb8, d.d_u8, npix * 3);
+    if (rc) return rc;
     BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
     return BSB_OK;
 }
@@ -523,7 +695,8 @@ namespace {
 
 // render on all GPUs + gather on GPU 0 + bloom; leaves the frame in devs[0].d_frame.
 // Records ev[0..4] on GPU 0: begin, own tile traced, gathered, bloomed.
-int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, bsb_stats *st)
+int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, bsb_stats *st, bool want_float,
+                       bool want_rgb8)
 {
     if (!cam || !scn) return fail(ctx, BSB_ERR_INVALID, "bsb_render_full: NULL argument");
     if (scn->width <= 0 || scn->height <= 0) return fail(ctx, BSB_ERR_INVALID, "resolution must be positive");
@@ -586,10 +759,19 @@ int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn
     BSB_CUDA(ctx, cudaSetDevice(d0.dev));
     BSB_CUDA(ctx, cudaEventRecord(d0.ev[2], d0.stream));
     // app/Main.hs:113: bloom only if bloomStrength /= 0
-    if (scn->bloom_strength != 0) {
-        rc = bloom_async(ctx, d0, scn->bloom_strength, scn->bloom_divider, W, H, d0.d_frame, d0.d_frame);
+    if (want_rgb8) {
+        rc = ensure(ctx, d0.d_u8, d0.u8_cap, npix * 3 + 16);
         if (rc) return rc;
-        launches += 2;
+    }
+    if (scn->bloom_strength != 0) {
+        // the sRGB + toWord8 map of writeImg rides in the epilogue of the second bloom launch; the
+        // float frame is only written if somebody wants it
+        rc = bloom_async(ctx, d0, scn->bloom_strength, scn->bloom_divider, W, H, d0.d_frame, want_float ? d0.d_frame : nullptr,
+                         want_rgb8 ? d0.d_u8 : nullptr, &launches);
+        if (rc) return rc;
+    } else if (want_rgb8) {
+        BSB_CUDA(ctx, launch_srgb8(d0.d_frame, d0.d_u8, d0.d_thr, npix, d0.stream));
+        launches += 1;
     }
     BSB_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
     if (st) { st->launches = launches; st->n_gpus = n; st->rays = rays_of(scn, H); }
@@ -633,11 +815,12 @@ extern "C" int bsb_render_full(bsb_ctx *ctx, const bsb_camera *cam, const bsb_sc
     const auto t0 = std::chrono::steady_clock::now();
     bsb_stats st;
     std::memset(&st, 0, sizeof st);
-    int rc = render_full_device(ctx, cam, scn, &st);
+    int rc = render_full_device(ctx, cam, scn, &st, true, false);
     if (rc) return rc;
     DeviceState &d0 = ctx->devs[0];
     const size_t npix = (size_t)scn->width * scn->height;
-    BSB_CUDA(ctx, cudaMemcpyAsync(out_rgba, d0.d_frame, npix * sizeof(float4), cudaMemcpyDeviceToHost, d0.stream));
+    rc = copy_to_host(ctx, d0, out_rgba, d0.d_frame, npix * sizeof(float4));
+    if (rc) return rc;
     BSB_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
     rc = collect_full_stats(ctx, &st);
     if (rc) return rc;
@@ -655,16 +838,12 @@ extern "C" int bsb_render_full_srgb8(bsb_ctx *ctx, const bsb_camera *cam, const 
     const auto t0 = std::chrono::steady_clock::now();
     bsb_stats st;
     std::memset(&st, 0, sizeof st);
-    int rc = render_full_device(ctx, cam, scn, &st);
+    int rc = render_full_device(ctx, cam, scn, &st, false, true);
     if (rc) return rc;
     DeviceState &d0 = ctx->devs[0];
     const size_t npix = (size_t)scn->width * scn->height;
-    rc = ensure(ctx, d0.d_u8, d0.u8_cap, npix * 3 + 16);
+    rc = copy_to_host(ctx, d0, out_rgb8, d0.d_u8, npix * 3);  // bloom_ms includes the fused sRGB map
     if (rc) return rc;
-    BSB_CUDA(ctx, launch_srgb8(d0.d_frame, d0.d_u8, npix, d0.stream));
-    st.launches += 1;
-    BSB_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));  // bloom_ms then includes the sRGB map
-    BSB_CUDA(ctx, cudaMemcpyAsync(out_rgb8, d0.d_u8, npix * 3, cudaMemcpyDeviceToHost, d0.stream));
     BSB_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
     rc = collect_full_stats(ctx, &st);
     if (rc) return rc;

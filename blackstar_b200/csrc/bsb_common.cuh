@@ -101,6 +101,31 @@ struct FrameParams {
     uint32_t pad1_;
 };
 
+// Arguments of the bloom line kernel (image_kernels.cu: box3_kernel).  A "line" is a row of the
+// image in the H launch and a column in the V launch.  A line may be assembled from up to
+// kMaxSegments pieces (multi-GPU: the column of an H^3-filtered frame whose row tiles came from
+// different GPUs), and only positions [x_lo, x_hi) of it are written (the rest is halo).
+constexpr int kMaxSegments = 8;
+#if defined(__CUDACC__)
+struct BoxArgs {
+    const float4 *seg_in[kMaxSegments];   // piece s of line l = seg_in[s] + l * seg_pitch[s]; it holds
+    size_t seg_pitch[kMaxSegments];       //   positions [seg_start[s], seg_start[s+1]) of the line
+    int seg_start[kMaxSegments + 1];
+    int nseg;
+    int n, lines;         // line length, number of lines
+    int x_lo, x_hi;       // positions of each line that are written
+    float4 *out;          // result of (line l, position x) -> out[(x - x_lo) * out_pitch + l]  (may be null)
+    const float4 *img;    // combine: indexed like out; may alias out
+    uint8_t *rgb8;        // optional: sRGB8 of the result at rgb8[(x - x_lo) * rgb8_pitch + 3 * l]
+    const float *thr;     // 256 floats: sRGB8 thresholds (host_setup.cpp: srgb8_thresholds)
+    size_t out_pitch, rgb8_pitch;
+    int r;                // box radius (src/ImageFilters.hs:83)
+    int combine;          // out = img + strength * blur (src/ImageFilters.hs:85-86)
+    float norm;           // 1 / (2r+1)   (src/ImageFilters.hs:51)
+    float strength;
+};
+#endif
+
 // Per-launch counters (device memory, zeroed before the launch).
 struct TraceCounters {
     unsigned long long steps;

@@ -51,6 +51,33 @@ void hue_coefficients(double hp, double k[3])
     }
 }
 
+// src/Raytracer.hs:23-27 sRGB, then massiv-io toWord8 = round-half-even (255 * clamp01 x)
+int srgb8_level_host(float xf)
+{
+    const double x = (double)xf;
+    const double a = 0.055;
+    const double s = x < 0.0031308 ? 12.92 * x : (1 + a) * std::pow(x, 1.0 / 2.4) - a;
+    double c = s < 0 ? 0 : (s > 1 ? 1 : s);
+    if (s != s) c = 0;
+    return (int)std::nearbyint(255 * c);
+}
+
+void srgb8_thresholds(float thr[256])
+{
+    thr[0] = 0.0f;
+    for (int k = 1; k < 256; k++) {
+        // non-negative floats order like their bit patterns; level(0) = 0 < k <= 255 = level(1)
+        uint32_t lo = 0u, hi = 0x3f800000u;  // level(lo) < k <= level(hi)
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            float f;
+            std::memcpy(&f, &mid, 4);
+            if (srgb8_level_host(f) >= k) hi = mid; else lo = mid;
+        }
+        std::memcpy(&thr[k], &hi, 4);
+    }
+}
+
 std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int row0, int row1, FrameParams &P)
 {
     if (scn.width <= 0 || scn.height <= 0) return "resolution must be positive";

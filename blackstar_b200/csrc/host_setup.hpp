@@ -36,4 +36,10 @@ bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std
 void host_hsi_to_rgb(double h, double s, double i, double rgb[3]);
 void hue_coefficients(double hue, double k[3]);
 
+// writeImg's map (src/Raytracer.hs:23-32) as a table: thr[k], k = 1..255, is the smallest float x
+// with toWord8(sRGB(x)) >= k (thr[0] = 0).  The map is monotone, so level(x) = #{k >= 1 : thr[k] <= x}.
+// Found by bisection over float bit patterns on the reference's double arithmetic.
+void srgb8_thresholds(float thr[256]);
+int srgb8_level_host(float x);
+
 }  // namespace bsb
