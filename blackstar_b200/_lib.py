@@ -18,7 +18,8 @@ SYMBOLS = [
     "bsb_set_option", "bsb_set_stars", "bsb_set_stars_ppm", "bsb_star_count", "bsb_render",
     "bsb_render_device", "bsb_bloom", "bsb_bloom_device", "bsb_render_full", "bsb_to_srgb8",
     "bsb_to_srgb8_device", "bsb_render_full_srgb8", "bsb_measure_fp64_peak", "bsb_measure_hbm_copy",
-    "bsb_selftest_rinv5",
+    "bsb_selftest_rinv5", "bsb_render_full_both", "bsb_render_full_device", "bsb_synchronize",
+    "bsb_bloom_h_device", "bsb_bloom_v_device", "bsb_bloom_to_device", "bsb_download_2d",
 ]
 
 
@@ -75,6 +76,13 @@ def load() -> ctypes.CDLL:
     L.bsb_to_srgb8.argtypes = [vp, i, i, vp, vp]; L.bsb_to_srgb8.restype = i
     L.bsb_to_srgb8_device.argtypes = [vp, i, i, vp, vp]; L.bsb_to_srgb8_device.restype = i
     L.bsb_render_full_srgb8.argtypes = [vp, vp, vp, vp, vp]; L.bsb_render_full_srgb8.restype = i
+    L.bsb_render_full_both.argtypes = [vp, vp, vp, vp, vp, vp]; L.bsb_render_full_both.restype = i
+    L.bsb_render_full_device.argtypes = [vp, vp, vp, i, i]; L.bsb_render_full_device.restype = i
+    L.bsb_synchronize.argtypes = [vp]; L.bsb_synchronize.restype = i
+    L.bsb_bloom_h_device.argtypes = [vp, i, i, i, vp, vp, vp]; L.bsb_bloom_h_device.restype = i
+    L.bsb_bloom_v_device.argtypes = [vp, d, i, i, i, i, vp, vp, vp, vp, vp]; L.bsb_bloom_v_device.restype = i
+    L.bsb_bloom_to_device.argtypes = [vp, d, i, i, i, vp, vp, vp]; L.bsb_bloom_to_device.restype = i
+    L.bsb_download_2d.argtypes = [vp, vp, sz, vp, sz, sz, i]; L.bsb_download_2d.restype = i
     L.bsb_measure_fp64_peak.argtypes = [vp, dp]; L.bsb_measure_fp64_peak.restype = i
     L.bsb_measure_hbm_copy.argtypes = [vp, sz, i, dp]; L.bsb_measure_hbm_copy.restype = i
     L.bsb_selftest_rinv5.argtypes = [vp, d, d, i, dp, dp]; L.bsb_selftest_rinv5.restype = i

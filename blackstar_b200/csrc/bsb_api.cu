@@ -34,6 +34,7 @@ cudaError_t launch_trace(const FrameParams &P, float4 *out, TraceCounters *ctr, 
 cudaError_t launch_ray_tables(const FrameParams &P, double *vx, double *vy, cudaStream_t stream);
 cudaError_t launch_rinv5_selftest(double q_lo, double q_hi, int n, double *d_out2, cudaStream_t stream);
 cudaError_t launch_box3(const BoxArgs &A, cudaStream_t stream);
+cudaError_t launch_transpose(const float4 *in, float4 *out, int rows, int cols, size_t in_pitch, size_t out_pitch, cudaStream_t stream);
 cudaError_t launch_bloom_long(const float4 *img, float4 *out, uint8_t *rgb8, const float *thr, float4 *tmp_a, float4 *tmp_b,
                               int W, int H, int r, float strength, cudaStream_t stream);
 int bloom_max_line();
@@ -163,8 +164,14 @@ struct DeviceState {
     float4 *d_tmp = nullptr;   size_t tmp_cap = 0;    // bloom's transposed intermediate
     float4 *d_tmp2 = nullptr;  size_t tmp2_cap = 0;   // second scratch frame of the long-line bloom
     float *d_thr = nullptr;                           // sRGB8 thresholds (256 floats)
-    uint8_t *h_stage = nullptr;                       // kStageSlots pinned chunks for copies into pageable memory
-    cudaEvent_t stage_ev[kStageSlots] = {};
+    cudaEvent_t stage_ev[kStageSlots] = {};           // "my part of staging slot s has landed"
+    // multi-GPU bloom: H^3 of my row tile and the tile itself, both transposed ([W][rows]); what the
+    // other GPUs sent me for my column band ([cols][H] in row-tile pieces); my band of the result
+    float4 *d_mid = nullptr;   size_t mid_cap = 0;
+    float4 *d_imgT = nullptr;  size_t imgT_cap = 0;
+    float4 *d_rmid = nullptr;  size_t rmid_cap = 0;
+    float4 *d_rimg = nullptr;  size_t rimg_cap = 0;
+    float4 *d_band = nullptr;  size_t band_cap = 0;
     float4 *d_aux = nullptr;   size_t aux_cap = 0;    // staging for host-buffer bloom / srgb
     uint8_t *d_u8 = nullptr;   size_t u8_cap = 0;
     double *d_vx = nullptr;    size_t vx_cap = 0;     // per-frame ray tables
@@ -185,6 +192,7 @@ struct bsb_ctx {
     NcclApi nccl;
     std::vector<ncclComm_t> comms;
     std::unique_ptr<CopyPool> pool;   // created on the first copy into pageable memory
+    uint8_t *h_stage = nullptr;       // kStageSlots pinned (portable) chunks for copies into pageable memory
     int copy_threads = 4;
     uint32_t step_cap = 0;            // 0 = the default of make_frame_params
 };
@@ -236,6 +244,7 @@ int trace_async(bsb_ctx *ctx, DeviceState &d, const bsb_camera *cam, const bsb_s
     FrameParams P;
     const std::string msg = make_frame_params(*cam, *scn, row0, row1, P);
     if (!msg.empty()) return fail(ctx, BSB_ERR_INVALID, msg);
+    if (ctx->step_cap) P.step_cap = ctx->step_cap;
     P.tree.top = d.d_top;
     P.tree.rec = d.d_rec;
     P.tree.stars = d.d_stars;
@@ -303,69 +312,120 @@ int bloom_async(bsb_ctx *ctx, DeviceState &d, double strength, int divider, int 
     return BSB_OK;
 }
 
-// Device -> caller-owned host memory, asynchronously ordered on d.stream up to the point where the
-// bytes have left the device; returns after the last byte is in `dst` only for pageable targets.
-//  * page-locked target (cudaHostAlloc / cudaHostRegister, e.g. GHC's pinned ForeignPtr registered by
-//    the shim, or torch's pinned tensors): one cudaMemcpyAsync, the DMA engine writes it directly;
+// One GPU's contribution to a host frame: rows [row0, row0+rows) x bytes [x_off, x_off+band_bytes)
+// of every such row, read from device memory laid out [rows][band_bytes].
+struct Band {
+    DeviceState *d;
+    const uint8_t *src;
+    size_t x_off, band_bytes;
+    int row0, rows;
+};
+
+// Device(s) -> caller-owned host frame of `rows` rows of `row_bytes` bytes; every band is ordered
+// after the work already queued on its GPU's stream.  Returns once the copies are QUEUED for a
+// page-locked target and once the bytes are in `dst` for a pageable one.
+//  * page-locked target (cudaHostAlloc / cudaHostRegister, e.g. torch's pinned tensors or a buffer
+//    the Haskell shim registered): every GPU's DMA engine writes its band directly, in parallel;
 //  * pageable target (plain malloc, what mallocForeignPtrBytes hands to the FFI): a cudaMemcpy to
 //    pageable memory is staged by the driver through one small buffer and runs at a fraction of the
-//    link rate, so the library stages it itself -- the frame is cut into 8 MB chunks that go through
-//    a ring of pinned buffers while a few parked host threads move finished chunks into the caller's
-//    buffer, so the PCIe transfer and the host copy overlap.
-int copy_to_host(bsb_ctx *ctx, DeviceState &d, void *dst, const void *src_dev, size_t bytes)
+//    link rate, so the library stages it itself -- the frame is cut into ~8 MB groups of rows that go
+//    through a ring of pinned buffers while a few parked host threads move finished groups into the
+//    caller's buffer, so the PCIe transfers and the host copy overlap.
+int copy_bands_to_host(bsb_ctx *ctx, void *dst, size_t row_bytes, int rows, const std::vector<Band> &bands)
 {
-    if (bytes == 0) return BSB_OK;
-    BSB_CUDA(ctx, cudaSetDevice(d.dev));
+    if (rows <= 0 || row_bytes == 0 || bands.empty()) return BSB_OK;
+    uint8_t *out = static_cast<uint8_t *>(dst);
+    const size_t bytes = row_bytes * (size_t)rows;
     cudaPointerAttributes attr;
     const cudaError_t pe = cudaPointerGetAttributes(&attr, dst);
     if (pe != cudaSuccess) (void)cudaGetLastError();
     const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     if (pinned || bytes < kStageChunk / 4 || ctx->copy_threads <= 0) {
-        BSB_CUDA(ctx, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, d.stream));
+        for (const Band &b : bands) {
+            BSB_CUDA(ctx, cudaSetDevice(b.d->dev));
+            uint8_t *row = out + (size_t)b.row0 * row_bytes;
+            if (b.band_bytes == row_bytes)
+                BSB_CUDA(ctx, cudaMemcpyAsync(row, b.src, row_bytes * (size_t)b.rows, cudaMemcpyDeviceToHost, b.d->stream));
+            else
+                BSB_CUDA(ctx, cudaMemcpy2DAsync(row + b.x_off, row_bytes, b.src, b.band_bytes, b.band_bytes, (size_t)b.rows,
+                                                cudaMemcpyDeviceToHost, b.d->stream));
+        }
         return BSB_OK;
     }
-    if (!d.h_stage) {
-        BSB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&d.h_stage), kStageSlots * kStageChunk, cudaHostAllocDefault));
-        for (auto &e : d.stage_ev) BSB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    if (!ctx->h_stage)
+        BSB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_stage), kStageSlots * kStageChunk, cudaHostAllocPortable));
+    for (const Band &b : bands)
+        if (!b.d->stage_ev[0]) {
+            BSB_CUDA(ctx, cudaSetDevice(b.d->dev));
+            for (auto &e : b.d->stage_ev) BSB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
     if (!ctx->pool || ctx->pool->size() != ctx->copy_threads) ctx->pool.reset(new CopyPool(ctx->copy_threads));
-    const int nchunks = (int)((bytes + kStageChunk - 1) / kStageChunk);
+    if (row_bytes > kStageChunk) return fail(ctx, BSB_ERR_UNSUPPORTED, "image row above 8 MB");
+    const int rows_per_chunk = (int)std::max<size_t>(1, kStageChunk / row_bytes);
+    const int nchunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
     const int nt = ctx->pool->size();
     std::vector<std::atomic<int>> copied(nchunks);
     for (auto &c : copied) c.store(0, std::memory_order_relaxed);
     std::atomic<int> enqueued{ 0 };
     std::atomic<int> failed{ 0 };
-    uint8_t *out = static_cast<uint8_t *>(dst);
+    uint8_t *stage = ctx->h_stage;
     ctx->pool->begin([&, nt](int k) {
-        cudaSetDevice(d.dev);
         for (int i = 0; i < nchunks; i++) {
             while (enqueued.load(std::memory_order_acquire) <= i) {
                 if (failed.load(std::memory_order_relaxed)) return;
                 std::this_thread::yield();
             }
-            if (cudaEventSynchronize(d.stage_ev[i % kStageSlots]) != cudaSuccess) failed.store(1);
-            const size_t off = (size_t)i * kStageChunk;
-            const size_t len = std::min(kStageChunk, bytes - off);
-            const size_t a = len * k / nt, b = len * (k + 1) / nt;   // my slice of the chunk
-            std::memcpy(out + off + a, d.h_stage + (size_t)(i % kStageSlots) * kStageChunk + a, b - a);
+            for (const Band &b : bands)
+                if (cudaEventSynchronize(b.d->stage_ev[i % kStageSlots]) != cudaSuccess) failed.store(1);
+            const int ya = i * rows_per_chunk, yb = std::min(rows, ya + rows_per_chunk);
+            const size_t len = (size_t)(yb - ya) * row_bytes;
+            const size_t a = len * k / nt, e = len * (k + 1) / nt;   // my slice of the group of rows
+            std::memcpy(out + (size_t)ya * row_bytes + a, stage + (size_t)(i % kStageSlots) * kStageChunk + a, e - a);
             copied[i].fetch_add(1, std::memory_order_release);
         }
     });
     cudaError_t err = cudaSuccess;
     for (int i = 0; i < nchunks && err == cudaSuccess; i++) {
-        if (i >= kStageSlots)   // the slot is free once every thread has copied its slice of chunk i - slots
+        if (i >= kStageSlots)   // the slot is free once every thread has copied its slice of group i - slots
             while (copied[i - kStageSlots].load(std::memory_order_acquire) < nt) std::this_thread::yield();
-        const size_t off = (size_t)i * kStageChunk;
-        const size_t len = std::min(kStageChunk, bytes - off);
-        err = cudaMemcpyAsync(d.h_stage + (size_t)(i % kStageSlots) * kStageChunk, static_cast<const uint8_t *>(src_dev) + off, len,
-                              cudaMemcpyDeviceToHost, d.stream);
-        if (err == cudaSuccess) err = cudaEventRecord(d.stage_ev[i % kStageSlots], d.stream);
+        const int ya = i * rows_per_chunk, yb = std::min(rows, ya + rows_per_chunk);
+        uint8_t *slot = stage + (size_t)(i % kStageSlots) * kStageChunk;
+        for (const Band &b : bands) {
+            if (err != cudaSuccess) break;
+            err = cudaSetDevice(b.d->dev);
+            const int y0 = std::max(ya, b.row0), y1 = std::min(yb, b.row0 + b.rows);
+            if (err == cudaSuccess && y1 > y0)
+                err = cudaMemcpy2DAsync(slot + (size_t)(y0 - ya) * row_bytes + b.x_off, row_bytes,
+                                        b.src + (size_t)(y0 - b.row0) * b.band_bytes, b.band_bytes, b.band_bytes, (size_t)(y1 - y0),
+                                        cudaMemcpyDeviceToHost, b.d->stream);
+            if (err == cudaSuccess) err = cudaEventRecord(b.d->stage_ev[i % kStageSlots], b.d->stream);
+        }
         if (err == cudaSuccess) enqueued.store(i + 1, std::memory_order_release);
     }
     if (err != cudaSuccess) failed.store(1);
     ctx->pool->wait();
     if (err != cudaSuccess) return fail(ctx, BSB_ERR_CUDA, std::string("staged device-to-host copy: ") + cudaGetErrorString(err));
     if (failed.load()) return fail(ctx, BSB_ERR_CUDA, "staged device-to-host copy failed");
+    return BSB_OK;
+}
+
+int copy_to_host(bsb_ctx *ctx, DeviceState &d, void *dst, const void *src_dev, size_t bytes)
+{
+    if (bytes == 0) return BSB_OK;
+    // a flat buffer is a frame of 1 MB rows (the last one ragged: copied as its own band)
+    const size_t rb = (size_t)1 << 20;
+    const int full = (int)(bytes / rb);
+    const uint8_t *src = static_cast<const uint8_t *>(src_dev);
+    if (full > 0) {
+        std::vector<Band> bands{ Band{ &d, src, 0, rb, 0, full } };
+        const int rc = copy_bands_to_host(ctx, dst, rb, full, bands);
+        if (rc) return rc;
+    }
+    if (bytes > (size_t)full * rb) {
+        BSB_CUDA(ctx, cudaSetDevice(d.dev));
+        BSB_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(dst) + (size_t)full * rb, src + (size_t)full * rb, bytes - (size_t)full * rb,
+                                      cudaMemcpyDeviceToHost, d.stream));
+    }
     return BSB_OK;
 }
 
@@ -400,8 +460,21 @@ extern "C" bsb_ctx *bsb_create_on(const int *devices, int n)
     }
     if (n <= 0 || !devices) { g_create_error = "empty device list"; return nullptr; }
     bsb_ctx *ctx = new bsb_ctx();
-    const char *v = std::getenv("BSB_TRACE_VARIANT");
-    if (v) ctx->trace_variant = std::atoi(v);
+    if (const char *v = std::getenv("BSB_TRACE_VARIANT")) {   // same range check as bsb_set_option
+        char *end = nullptr;
+        const long x = std::strtol(v, &end, 10);
+        if (end == v || *end != 0 || x < 0 || x > 6 || x == 5) {
+            g_create_error = "BSB_TRACE_VARIANT must be 0..4 or 6";
+            delete ctx;
+            return nullptr;
+        }
+        ctx->trace_variant = (int)x;
+    }
+    if (n > kMaxSegments) {
+        g_create_error = "at most 8 GPUs per context (one NVSwitch box)";
+        delete ctx;
+        return nullptr;
+    }
     float thr[256];
     srgb8_thresholds(thr);
     for (int k = 0; k < n; k++) {
@@ -470,10 +543,19 @@ extern "C" bsb_ctx *bsb_create(int n_gpus)
         return nullptr;
     }
     if (n_gpus < 0 || n_gpus > count) { g_create_error = "n_gpus exceeds the visible devices"; return nullptr; }
-    if (n_gpus == 0) n_gpus = count;
+    const bool all = n_gpus == 0;
+    if (all) n_gpus = std::min(count, kMaxSegments);
     std::vector<int> devs(n_gpus);
     for (int k = 0; k < n_gpus; k++) devs[k] = k;
-    return bsb_create_on(devs.data(), n_gpus);
+    bsb_ctx *ctx = bsb_create_on(devs.data(), n_gpus);
+    if (!ctx && all && n_gpus > 1) {
+        // "every visible device" is a wish, not a requirement: without a loadable NCCL fall back to one GPU
+        const std::string why = g_create_error;
+        ctx = bsb_create_on(devs.data(), 1);
+        if (ctx) std::fprintf(stderr, "blackstar_b200: multi-GPU context failed (%s); using device 0 only\n", why.c_str());
+        else g_create_error = why;
+    }
+    return ctx;
 }
 
 extern "C" void bsb_destroy(bsb_ctx *ctx)
@@ -491,8 +573,12 @@ extern "C" void bsb_destroy(bsb_ctx *ctx)
         if (d.d_tmp) cudaFree(d.d_tmp);
         if (d.d_tmp2) cudaFree(d.d_tmp2);
         if (d.d_thr) cudaFree(d.d_thr);
-        if (d.h_stage) cudaFreeHost(d.h_stage);
         for (auto &e : d.stage_ev) if (e) cudaEventDestroy(e);
+        if (d.d_mid) cudaFree(d.d_mid);
+        if (d.d_imgT) cudaFree(d.d_imgT);
+        if (d.d_rmid) cudaFree(d.d_rmid);
+        if (d.d_rimg) cudaFree(d.d_rimg);
+        if (d.d_band) cudaFree(d.d_band);
         if (d.d_aux) cudaFree(d.d_aux);
         if (d.d_u8) cudaFree(d.d_u8);
         if (d.d_vx) cudaFree(d.d_vx);
@@ -501,6 +587,8 @@ extern "C" void bsb_destroy(bsb_ctx *ctx)
         for (auto &ev : d.ev) if (ev) cudaEventDestroy(ev);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
     }
+    ctx->pool.reset();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
 }
 
@@ -520,6 +608,16 @@ extern "C" int bsb_set_option(bsb_ctx *ctx, const char *key, double value)
     if (std::strcmp(key, "trace_variant") == 0) {
         if (value < 0 || value > 6 || (int)value == 5) return fail(ctx, BSB_ERR_INVALID, "trace_variant must be 0..4 or 6");
         ctx->trace_variant = (int)value;
+        return BSB_OK;
+    }
+    if (std::strcmp(key, "copy_threads") == 0) {
+        if (value < 0 || value > 64) return fail(ctx, BSB_ERR_INVALID, "copy_threads must be 0..64 (0 = leave pageable copies to the driver)");
+        ctx->copy_threads = (int)value;
+        return BSB_OK;
+    }
+    if (std::strcmp(key, "step_cap") == 0) {
+        if (value < 1 || value > 4294967295.0) return fail(ctx, BSB_ERR_INVALID, "step_cap must be 1..2^32-1");
+        ctx->step_cap = (uint32_t)value;
         return BSB_OK;
     }
     return fail(ctx, BSB_ERR_INVALID, std::string("unknown option ") + key);
@@ -693,77 +791,117 @@ extern "C" int bsb_to_srgb8(bsb_ctx *ctx, int width, int height, const float *in
 // ======================================================================== doRender
 namespace {
 
-// render on all GPUs + gather on GPU 0 + bloom; leaves the frame in devs[0].d_frame.
-// Records ev[0..4] on GPU 0: begin, own tile traced, gathered, bloomed.
-int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, bsb_stats *st, bool want_float,
-                       bool want_rgb8)
+// Contiguous row tiles.  First frame: equal shares.  Afterwards: proportional to the rate every GPU
+// achieved on its previous tile (rows per millisecond), so that tiles with fewer RK4 steps per ray
+// (the hole, the far sky) get more rows and all GPUs finish together.  Boundaries are even.
+void plan_row_tiles(bsb_ctx *ctx, int H, std::vector<int> &r0, std::vector<int> &r1)
 {
-    if (!cam || !scn) return fail(ctx, BSB_ERR_INVALID, "bsb_render_full: NULL argument");
-    if (scn->width <= 0 || scn->height <= 0) return fail(ctx, BSB_ERR_INVALID, "resolution must be positive");
     const int n = (int)ctx->devs.size();
+    r0.assign(n, 0); r1.assign(n, 0);
+    double total_rate = 0;
+    bool known = n > 1;
+    for (int k = 0; k < n; k++) { known = known && ctx->devs[k].rows_per_ms > 0; total_rate += ctx->devs[k].rows_per_ms; }
+    double acc = 0;
+    for (int k = 0; k < n; k++) {
+        r0[k] = k == 0 ? 0 : r1[k - 1];
+        int e;
+        if (known) {
+            acc += ctx->devs[k].rows_per_ms / total_rate;
+            e = (int)(acc * H + 0.5);
+        } else {
+            e = (int)((long long)H * (k + 1) / n);
+        }
+        e &= ~1;
+        r1[k] = k == n - 1 ? H : std::max(r0[k], std::min(H, e));
+    }
+}
+
+int bloom_radius(bsb_ctx *ctx, int w, int h, int divider, int *r)
+{
+    if (w <= 0 || h <= 0) return fail(ctx, BSB_ERR_INVALID, "bloom: image size must be positive");
+    if (divider <= 0) return fail(ctx, BSB_ERR_INVALID, "bloom: bloomDivider must be positive (`div` by zero in the reference)");
+    *r = w / divider;  // src/ImageFilters.hs:83
+    if (*r < 1)
+        return fail(ctx, BSB_ERR_INVALID,
+                    "bloom: radius 0 (width < bloomDivider); the reference's boxBlur fails here (foldl1' of an empty window)");
+    return BSB_OK;
+}
+
+// H^3 of `rows` rows of width w on device d: src [rows][w] -> midT [w][rows]; imgT (optional) = src transposed
+int bloom_h_async(bsb_ctx *ctx, DeviceState &d, int r, int w, int rows, const float4 *src, float4 *midT, float4 *imgT)
+{
+    if (rows <= 0) return BSB_OK;
+    if (w > bloom_max_line()) return fail(ctx, BSB_ERR_UNSUPPORTED, "bloom: rows longer than 8192 pixels take the single-GPU path");
+    BSB_CUDA(ctx, cudaSetDevice(d.dev));
+    BoxArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.r = r;
+    A.norm = (float)(1.0 / (2.0 * (double)r + 1.0));
+    A.nseg = 1; A.seg_in[0] = src; A.seg_pitch[0] = (size_t)w; A.seg_start[0] = 0; A.seg_start[1] = w;
+    A.out = midT; A.out_pitch = (size_t)rows;
+    A.n = w; A.lines = rows; A.x_lo = 0; A.x_hi = w;
+    BSB_CUDA(ctx, launch_box3(A, d.stream));
+    if (imgT) BSB_CUDA(ctx, launch_transpose(src, imgT, rows, w, (size_t)w, (size_t)rows, d.stream));
+    return BSB_OK;
+}
+
+// V^3 + combine (+ sRGB8) of `cols` columns of height h on device d.  Column l is assembled from nseg
+// pieces: piece s = seg_mid[s] + l * seg_rows[s] holds rows [sum of seg_rows before s, ...) of it;
+// seg_img is the unfiltered image laid out the same way.  out [h][cols] float4 and / or rgb8 [h][cols*3].
+int bloom_v_async(bsb_ctx *ctx, DeviceState &d, double strength, int r, int h, int cols, int nseg, const float4 *const *seg_mid,
+                  const float4 *const *seg_img, const int *seg_rows, float4 *out, uint8_t *rgb8)
+{
+    if (cols <= 0 || h <= 0) return BSB_OK;
+    if (nseg < 1 || nseg > kMaxSegments) return fail(ctx, BSB_ERR_INVALID, "bloom: 1..8 row segments");
+    if (h > bloom_max_line()) return fail(ctx, BSB_ERR_UNSUPPORTED, "bloom: columns longer than 8192 pixels take the single-GPU path");
+    BSB_CUDA(ctx, cudaSetDevice(d.dev));
+    BoxArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.r = r;
+    A.norm = (float)(1.0 / (2.0 * (double)r + 1.0));
+    A.thr = d.d_thr;
+    int y = 0, m = 0;
+    for (int s = 0; s < nseg; s++) {
+        if (seg_rows[s] < 0) return fail(ctx, BSB_ERR_INVALID, "bloom: negative segment");
+        if (seg_rows[s] == 0) continue;
+        A.seg_in[m] = seg_mid[s]; A.seg_img[m] = seg_img[s]; A.seg_pitch[m] = (size_t)seg_rows[s]; A.seg_start[m] = y;
+        y += seg_rows[s];
+        m++;
+    }
+    if (y != h) return fail(ctx, BSB_ERR_INVALID, "bloom: the row segments do not add up to the image height");
+    A.seg_start[m] = h;
+    A.nseg = m;
+    A.out = out; A.out_pitch = (size_t)cols; A.rgb8 = rgb8; A.rgb8_pitch = (size_t)cols * 3;
+    A.n = h; A.lines = cols; A.x_lo = 0; A.x_hi = h; A.combine = 2; A.strength = (float)strength;
+    BSB_CUDA(ctx, launch_box3(A, d.stream));
+    return BSB_OK;
+}
+
+struct FullResult {
+    std::vector<Band> f32, u8;   // where the frame is (device memory), as bands of the host frame
+};
+
+// One GPU: trace -> bloom (2 launches, sRGB8 fused) -> frame in d_frame / d_u8.
+int render_full_single(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, bsb_stats *st, bool want_float, bool want_rgb8,
+                       FullResult &res)
+{
     const int W = scn->width, H = scn->height;
     const size_t npix = (size_t)W * H;
     DeviceState &d0 = ctx->devs[0];
     BSB_CUDA(ctx, cudaSetDevice(d0.dev));
     int rc = ensure(ctx, d0.d_frame, d0.frame_cap, npix);
     if (rc) return rc;
-    // Row tiles.  First frame: equal shares.  Afterwards: proportional to the rate every GPU
-    // achieved on its previous tile (rows per millisecond), so that tiles with fewer RK4 steps per
-    // ray (the hole, the far sky) get more rows and all GPUs finish together.
-    std::vector<int> r0(n), r1(n);
-    {
-        double total_rate = 0;
-        bool known = n > 1;
-        for (int k = 0; k < n; k++) { known = known && ctx->devs[k].rows_per_ms > 0; total_rate += ctx->devs[k].rows_per_ms; }
-        double acc = 0;
-        for (int k = 0; k < n; k++) {
-            r0[k] = k == 0 ? 0 : r1[k - 1];
-            if (known) {
-                acc += ctx->devs[k].rows_per_ms / total_rate;
-                r1[k] = k == n - 1 ? H : std::max(r0[k], std::min(H, (int)(acc * H + 0.5)));
-            } else {
-                r1[k] = (int)((long long)H * (k + 1) / n);
-            }
-        }
-    }
-    for (int k = 1; k < n; k++) {
-        DeviceState &d = ctx->devs[k];
-        BSB_CUDA(ctx, cudaSetDevice(d.dev));
-        rc = ensure(ctx, d.d_frame, d.frame_cap, (size_t)(r1[k] - r0[k]) * W + 1);
-        if (rc) return rc;
-    }
-    // row tiles: GPU k renders rows [H k/n, H (k+1)/n) of the final image
-    for (int k = 0; k < n; k++) {
-        DeviceState &d = ctx->devs[k];
-        float4 *dst = k == 0 ? d0.d_frame : d.d_frame;
-        rc = trace_async(ctx, d, cam, scn, r0[k], r1[k], dst, d.ev[0], d.ev[1]);
-        if (rc) return rc;
-        d.last_rows = r1[k] - r0[k];
-    }
-    int launches = 0;  // ray tables + trace on every GPU that has rows
-    for (int k = 0; k < n; k++) launches += r1[k] > r0[k] ? 2 : 0;
-    // the single collective of the path: gather the tiles on GPU 0 (grouped send/recv)
-    if (n > 1) {
-        int nrc = ctx->nccl.GroupStart();
-        for (int k = 1; k < n && nrc == 0; k++) {
-            const size_t cnt = (size_t)(r1[k] - r0[k]) * W * 4;
-            if (cnt == 0) continue;
-            nrc = ctx->nccl.Recv(d0.d_frame + (size_t)r0[k] * W, cnt, kNcclFloat, k, ctx->comms[0], d0.stream);
-            if (nrc == 0) nrc = ctx->nccl.Send(ctx->devs[k].d_frame, cnt, kNcclFloat, 0, ctx->comms[k], ctx->devs[k].stream);
-        }
-        const int erc = ctx->nccl.GroupEnd();
-        if (nrc == 0) nrc = erc;
-        if (nrc != 0) return fail(ctx, BSB_ERR_NCCL, std::string("NCCL gather: ") + ctx->nccl.GetErrorString(nrc));
-        BSB_CUDA(ctx, cudaSetDevice(d0.dev));
-    }
-    BSB_CUDA(ctx, cudaSetDevice(d0.dev));
+    rc = trace_async(ctx, d0, cam, scn, 0, H, d0.d_frame, d0.ev[0], d0.ev[1]);
+    if (rc) return rc;
+    d0.last_rows = H;
+    int launches = 2;
+    BSB_CUDA(ctx, cudaEventRecord(d0.ev[5], d0.stream));
     BSB_CUDA(ctx, cudaEventRecord(d0.ev[2], d0.stream));
-    // app/Main.hs:113: bloom only if bloomStrength /= 0
     if (want_rgb8) {
         rc = ensure(ctx, d0.d_u8, d0.u8_cap, npix * 3 + 16);
         if (rc) return rc;
     }
-    if (scn->bloom_strength != 0) {
+    if (scn->bloom_strength != 0) {   // app/Main.hs:113: bloom only if bloomStrength /= 0
         // the sRGB + toWord8 map of writeImg rides in the epilogue of the second bloom launch; the
         // float frame is only written if somebody wants it
         rc = bloom_async(ctx, d0, scn->bloom_strength, scn->bloom_divider, W, H, d0.d_frame, want_float ? d0.d_frame : nullptr,
@@ -774,34 +912,189 @@ int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn
         launches += 1;
     }
     BSB_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
-    if (st) { st->launches = launches; st->n_gpus = n; st->rays = rays_of(scn, H); }
+    if (want_float) res.f32.push_back(Band{ &d0, reinterpret_cast<const uint8_t *>(d0.d_frame), 0, (size_t)W * 16, 0, H });
+    if (want_rgb8) res.u8.push_back(Band{ &d0, d0.d_u8, 0, (size_t)W * 3, 0, H });
+    st->launches = launches; st->n_gpus = 1; st->rays = rays_of(scn, H);
     return BSB_OK;
 }
 
+// N GPUs.  Rays are independent, so GPU k traces a contiguous tile of rows.  The bloom is separable:
+//   H^3 needs whole rows  -> every GPU filters its own row tile (no communication);
+//   V^3 needs whole columns -> ONE all-to-all re-cuts the frame from row tiles into column bands
+//       (the H^3-filtered tile and the tile itself, both already transposed, go out in contiguous
+//       pieces); every GPU then filters its band, adds the original and maps it to sRGB8.
+// The finished frame is a set of column bands, one per GPU; N DMA engines copy them into the caller's
+// host frame in parallel.  (Without bloom the row tiles go straight to the host.)  Everything is
+// queued asynchronously; the only host synchronisation is at the end.
+int render_full_multi(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, bsb_stats *st, bool want_float, bool want_rgb8,
+                      FullResult &res)
+{
+    const int n = (int)ctx->devs.size();
+    const int W = scn->width, H = scn->height;
+    const bool bloom = scn->bloom_strength != 0;
+    int r = 0;
+    if (bloom) {
+        const int rc = bloom_radius(ctx, W, H, scn->bloom_divider, &r);
+        if (rc) return rc;
+        if (W > bloom_max_line() || H > bloom_max_line())
+            return fail(ctx, BSB_ERR_UNSUPPORTED, "multi-GPU bloom: image side above 8192 (use a 1-GPU ctx: it has the long-line path)");
+    }
+    std::vector<int> r0, r1, c0(n), c1(n);
+    plan_row_tiles(ctx, H, r0, r1);
+    for (int k = 0; k < n; k++) {   // column bands: equal, even boundaries
+        c0[k] = k == 0 ? 0 : c1[k - 1];
+        c1[k] = k == n - 1 ? W : std::max(c0[k], std::min(W, (int)((long long)W * (k + 1) / n) & ~1));
+    }
+    int launches = 0, rc;
+    for (int k = 0; k < n; k++) {
+        DeviceState &d = ctx->devs[k];
+        const int hk = r1[k] - r0[k], wk = c1[k] - c0[k];
+        BSB_CUDA(ctx, cudaSetDevice(d.dev));
+        if ((rc = ensure(ctx, d.d_frame, d.frame_cap, (size_t)hk * W + 1))) return rc;
+        if (bloom) {
+            if ((rc = ensure(ctx, d.d_mid, d.mid_cap, (size_t)hk * W + 1))) return rc;
+            if ((rc = ensure(ctx, d.d_imgT, d.imgT_cap, (size_t)hk * W + 1))) return rc;
+            if ((rc = ensure(ctx, d.d_rmid, d.rmid_cap, (size_t)wk * H + 1))) return rc;
+            if ((rc = ensure(ctx, d.d_rimg, d.rimg_cap, (size_t)wk * H + 1))) return rc;
+            if (want_float && (rc = ensure(ctx, d.d_band, d.band_cap, (size_t)wk * H + 1))) return rc;
+            if (want_rgb8 && (rc = ensure(ctx, d.d_u8, d.u8_cap, (size_t)wk * H * 3 + 16))) return rc;
+        } else if (want_rgb8) {
+            if ((rc = ensure(ctx, d.d_u8, d.u8_cap, (size_t)hk * W * 3 + 16))) return rc;
+        }
+        if ((rc = trace_async(ctx, d, cam, scn, r0[k], r1[k], d.d_frame, d.ev[0], d.ev[1]))) return rc;
+        d.last_rows = hk;
+        launches += hk > 0 ? 2 : 0;
+        if (bloom) {
+            if ((rc = bloom_h_async(ctx, d, r, W, hk, d.d_frame, d.d_mid, d.d_imgT))) return rc;
+            launches += hk > 0 ? 2 : 0;
+        } else if (want_rgb8 && hk > 0) {
+            BSB_CUDA(ctx, launch_srgb8(d.d_frame, d.d_u8, d.d_thr, (size_t)hk * W, d.stream));
+            launches += 1;
+        }
+        BSB_CUDA(ctx, cudaEventRecord(d.ev[5], d.stream));
+    }
+    if (!bloom) {
+        for (int k = 0; k < n; k++) {
+            DeviceState &d = ctx->devs[k];
+            BSB_CUDA(ctx, cudaSetDevice(d.dev));
+            BSB_CUDA(ctx, cudaEventRecord(d.ev[2], d.stream));
+            BSB_CUDA(ctx, cudaEventRecord(d.ev[3], d.stream));
+            const int hk = r1[k] - r0[k];
+            if (hk <= 0) continue;
+            if (want_float) res.f32.push_back(Band{ &d, reinterpret_cast<const uint8_t *>(d.d_frame), 0, (size_t)W * 16, r0[k], hk });
+            if (want_rgb8) res.u8.push_back(Band{ &d, d.d_u8, 0, (size_t)W * 3, r0[k], hk });
+        }
+        st->launches = launches; st->n_gpus = n; st->rays = rays_of(scn, H);
+        return BSB_OK;
+    }
+    // the single collective of the path: all-to-all of the transposed tiles (grouped send/recv).
+    // GPU i's tile, transposed, is [W][h_i]: the rows c0_j..c1_j of it are what GPU j needs -- contiguous.
+    {
+        int nrc = ctx->nccl.GroupStart();
+        for (int i = 0; i < n && nrc == 0; i++) {
+            const int hi = r1[i] - r0[i];
+            if (hi <= 0) continue;
+            DeviceState &di = ctx->devs[i];
+            for (int j = 0; j < n && nrc == 0; j++) {
+                const int wj = c1[j] - c0[j];
+                if (wj <= 0) continue;
+                DeviceState &dj = ctx->devs[j];
+                const size_t cnt = (size_t)wj * hi * 4;                   // floats
+                const size_t src_off = (size_t)c0[j] * hi;                // float4
+                const size_t dst_off = (size_t)wj * r0[i];                // float4: pieces in tile order
+                nrc = ctx->nccl.Send(di.d_mid + src_off, cnt, kNcclFloat, j, ctx->comms[i], di.stream);
+                if (nrc == 0) nrc = ctx->nccl.Recv(dj.d_rmid + dst_off, cnt, kNcclFloat, i, ctx->comms[j], dj.stream);
+                if (nrc == 0) nrc = ctx->nccl.Send(di.d_imgT + src_off, cnt, kNcclFloat, j, ctx->comms[i], di.stream);
+                if (nrc == 0) nrc = ctx->nccl.Recv(dj.d_rimg + dst_off, cnt, kNcclFloat, i, ctx->comms[j], dj.stream);
+            }
+        }
+        const int erc = ctx->nccl.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        if (nrc != 0) return fail(ctx, BSB_ERR_NCCL, std::string("NCCL all-to-all: ") + ctx->nccl.GetErrorString(nrc));
+    }
+    for (int j = 0; j < n; j++) {
+        DeviceState &d = ctx->devs[j];
+        const int wj = c1[j] - c0[j];
+        BSB_CUDA(ctx, cudaSetDevice(d.dev));
+        BSB_CUDA(ctx, cudaEventRecord(d.ev[2], d.stream));
+        const float4 *seg_mid[kMaxSegments], *seg_img[kMaxSegments];
+        int seg_rows[kMaxSegments];
+        for (int i = 0; i < n; i++) {
+            seg_mid[i] = d.d_rmid + (size_t)wj * r0[i];
+            seg_img[i] = d.d_rimg + (size_t)wj * r0[i];
+            seg_rows[i] = r1[i] - r0[i];
+        }
+        if ((rc = bloom_v_async(ctx, d, scn->bloom_strength, r, H, wj, n, seg_mid, seg_img, seg_rows, want_float ? d.d_band : nullptr,
+                                want_rgb8 ? d.d_u8 : nullptr)))
+            return rc;
+        launches += wj > 0 ? 1 : 0;
+        BSB_CUDA(ctx, cudaEventRecord(d.ev[3], d.stream));
+        if (wj <= 0) continue;
+        if (want_float) res.f32.push_back(Band{ &d, reinterpret_cast<const uint8_t *>(d.d_band), (size_t)c0[j] * 16, (size_t)wj * 16, 0, H });
+        if (want_rgb8) res.u8.push_back(Band{ &d, d.d_u8, (size_t)c0[j] * 3, (size_t)wj * 3, 0, H });
+    }
+    st->launches = launches; st->n_gpus = n; st->rays = rays_of(scn, H);
+    return BSB_OK;
+}
+
+int render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, bsb_stats *st, bool want_float, bool want_rgb8,
+                       FullResult &res)
+{
+    if (!cam || !scn) return fail(ctx, BSB_ERR_INVALID, "bsb_render_full: NULL argument");
+    if (scn->width <= 0 || scn->height <= 0) return fail(ctx, BSB_ERR_INVALID, "resolution must be positive");
+    if (ctx->devs.size() == 1) return render_full_single(ctx, cam, scn, st, want_float, want_rgb8, res);
+    return render_full_multi(ctx, cam, scn, st, want_float, want_rgb8, res);
+}
+
+// wait for every GPU, read the events and counters
 int collect_full_stats(bsb_ctx *ctx, bsb_stats *st)
 {
     const int n = (int)ctx->devs.size();
-    double trace_ms = 0;
+    double trace_ms = 0, post_ms = 0, xchg_ms = 0, d2h_ms = 0;
     for (int k = 0; k < n; k++) {
         DeviceState &d = ctx->devs[k];
         BSB_CUDA(ctx, cudaSetDevice(d.dev));
         BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
-        float ms = 0;
+        float ms = 0, a = 0, b = 0;
         BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
-        if (ms > trace_ms) trace_ms = ms;
+        trace_ms = std::max(trace_ms, (double)ms);
         d.rows_per_ms = (d.last_rows >= 8 && ms > 1e-3f) ? d.last_rows / (double)ms : 0.0;
+        BSB_CUDA(ctx, cudaEventElapsedTime(&a, d.ev[1], d.ev[5]));   // H^3 (+ transpose)
+        BSB_CUDA(ctx, cudaEventElapsedTime(&b, d.ev[2], d.ev[3]));   // V^3 + combine (or the whole bloom on one GPU)
+        post_ms = std::max(post_ms, (double)a + b);
+        BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev[5], d.ev[2]));  // all-to-all (includes waiting for the slowest tile)
+        xchg_ms = std::max(xchg_ms, (double)ms);
+        BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev[3], d.ev[4]));
+        d2h_ms = std::max(d2h_ms, (double)ms);
         fill_counter_stats(d, st);
     }
-    DeviceState &d0 = ctx->devs[0];
-    BSB_CUDA(ctx, cudaSetDevice(d0.dev));
-    float ms = 0;
     st->trace_ms = trace_ms;
-    BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[1], d0.ev[2]));
-    st->gather_ms = n > 1 ? ms : 0.0;
-    BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[2], d0.ev[3]));
-    st->bloom_ms = ms;
-    BSB_CUDA(ctx, cudaEventElapsedTime(&ms, d0.ev[3], d0.ev[4]));
-    st->d2h_ms = ms;
+    st->gather_ms = n > 1 ? xchg_ms : 0.0;
+    st->bloom_ms = post_ms;
+    st->d2h_ms = d2h_ms;
+    return BSB_OK;
+}
+
+int render_full_host(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, float *out_rgba, uint8_t *out_rgb8, bsb_stats *stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    bsb_stats st;
+    std::memset(&st, 0, sizeof st);
+    FullResult res;
+    int rc = render_full_device(ctx, cam, scn, &st, out_rgba != nullptr, out_rgb8 != nullptr, res);
+    if (rc) return rc;
+    const int W = scn->width, H = scn->height;
+    if (out_rgba && (rc = copy_bands_to_host(ctx, out_rgba, (size_t)W * 16, H, res.f32))) return rc;
+    if (out_rgb8 && (rc = copy_bands_to_host(ctx, out_rgb8, (size_t)W * 3, H, res.u8))) return rc;
+    for (DeviceState &d : ctx->devs) {
+        BSB_CUDA(ctx, cudaSetDevice(d.dev));
+        BSB_CUDA(ctx, cudaEventRecord(d.ev[4], d.stream));
+    }
+    rc = collect_full_stats(ctx, &st);
+    if (rc) return rc;
+    st.total_ms = ms_since(t0);
+    if (stats) *stats = st;
+    if (st.capped) return fail(ctx, BSB_ERR_STEPCAP, "a ray reached the step cap (the reference would not terminate)");
     return BSB_OK;
 }
 
@@ -812,22 +1105,7 @@ extern "C" int bsb_render_full(bsb_ctx *ctx, const bsb_camera *cam, const bsb_sc
 {
     if (!ctx) return BSB_ERR_INVALID;
     if (!out_rgba) return fail(ctx, BSB_ERR_INVALID, "bsb_render_full: NULL output buffer");
-    const auto t0 = std::chrono::steady_clock::now();
-    bsb_stats st;
-    std::memset(&st, 0, sizeof st);
-    int rc = render_full_device(ctx, cam, scn, &st, true, false);
-    if (rc) return rc;
-    DeviceState &d0 = ctx->devs[0];
-    const size_t npix = (size_t)scn->width * scn->height;
-    rc = copy_to_host(ctx, d0, out_rgba, d0.d_frame, npix * sizeof(float4));
-    if (rc) return rc;
-    BSB_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
-    rc = collect_full_stats(ctx, &st);
-    if (rc) return rc;
-    st.total_ms = ms_since(t0);
-    if (stats) *stats = st;
-    if (st.capped) return fail(ctx, BSB_ERR_STEPCAP, "a ray reached the step cap (the reference would not terminate)");
-    return BSB_OK;
+    return render_full_host(ctx, cam, scn, out_rgba, nullptr, stats);
 }
 
 extern "C" int bsb_render_full_srgb8(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, uint8_t *out_rgb8,
@@ -835,22 +1113,85 @@ extern "C" int bsb_render_full_srgb8(bsb_ctx *ctx, const bsb_camera *cam, const 
 {
     if (!ctx) return BSB_ERR_INVALID;
     if (!out_rgb8) return fail(ctx, BSB_ERR_INVALID, "bsb_render_full_srgb8: NULL output buffer");
-    const auto t0 = std::chrono::steady_clock::now();
+    return render_full_host(ctx, cam, scn, nullptr, out_rgb8, stats);
+}
+
+// Both images of one render (the float frame and its sRGB8 map) -- either pointer may be NULL.
+extern "C" int bsb_render_full_both(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, float *out_rgba,
+                                    uint8_t *out_rgb8, bsb_stats *stats)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    if (!out_rgba && !out_rgb8) return fail(ctx, BSB_ERR_INVALID, "bsb_render_full_both: no output buffer");
+    return render_full_host(ctx, cam, scn, out_rgba, out_rgb8, stats);
+}
+
+// The same work with the frame left on the GPUs (no host copy, no host synchronisation): what a
+// caller that keeps post-processing on the device uses, and what bench.py times as `value`.
+extern "C" int bsb_render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn, int want_float, int want_rgb8)
+{
+    if (!ctx) return BSB_ERR_INVALID;
     bsb_stats st;
     std::memset(&st, 0, sizeof st);
-    int rc = render_full_device(ctx, cam, scn, &st, false, true);
-    if (rc) return rc;
-    DeviceState &d0 = ctx->devs[0];
-    const size_t npix = (size_t)scn->width * scn->height;
-    rc = copy_to_host(ctx, d0, out_rgb8, d0.d_u8, npix * 3);  // bloom_ms includes the fused sRGB map
-    if (rc) return rc;
-    BSB_CUDA(ctx, cudaEventRecord(d0.ev[4], d0.stream));
-    rc = collect_full_stats(ctx, &st);
-    if (rc) return rc;
-    st.total_ms = ms_since(t0);
-    if (stats) *stats = st;
-    if (st.capped) return fail(ctx, BSB_ERR_STEPCAP, "a ray reached the step cap (the reference would not terminate)");
+    FullResult res;
+    return render_full_device(ctx, cam, scn, &st, want_float != 0, want_rgb8 != 0, res);
+}
+
+// Blocks until everything queued on the ctx's GPUs has finished.
+extern "C" int bsb_synchronize(bsb_ctx *ctx)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    for (DeviceState &d : ctx->devs) {
+        BSB_CUDA(ctx, cudaSetDevice(d.dev));
+        BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    }
     return BSB_OK;
+}
+
+// bloom + writeImg's map on device memory: out_rgba and / or out_rgb8 (either may be NULL)
+extern "C" int bsb_bloom_to_device(bsb_ctx *ctx, double strength, int divider, int width, int height, const void *dev_in,
+                                   void *dev_out_rgba, void *dev_out_rgb8)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    if (!dev_in || (!dev_out_rgba && !dev_out_rgb8)) return fail(ctx, BSB_ERR_INVALID, "bsb_bloom_to_device: NULL argument");
+    return bloom_async(ctx, ctx->devs[0], strength, divider, width, height, static_cast<const float4 *>(dev_in),
+                       static_cast<float4 *>(dev_out_rgba), static_cast<uint8_t *>(dev_out_rgb8));
+}
+
+// rows x width_bytes from device memory (pitch dev_pitch) into a host frame (pitch host_pitch), ordered
+// after the work queued on the ctx stream.  Page-locked host memory: asynchronous DMA; pageable: staged.
+extern "C" int bsb_download_2d(bsb_ctx *ctx, void *host_dst, size_t host_pitch, const void *dev_src, size_t dev_pitch,
+                               size_t width_bytes, int rows)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    if (rows < 0 || (rows > 0 && (!host_dst || !dev_src)) || width_bytes > host_pitch || dev_pitch != width_bytes)
+        return fail(ctx, BSB_ERR_INVALID, "bsb_download_2d: bad argument (the device rows must be dense)");
+    if (rows == 0 || width_bytes == 0) return BSB_OK;
+    std::vector<Band> bands{ Band{ &ctx->devs[0], static_cast<const uint8_t *>(dev_src), 0, width_bytes, 0, rows } };
+    return copy_bands_to_host(ctx, host_dst, host_pitch, rows, bands);
+}
+
+// ---- building blocks of the distributed bloom for one-process-per-GPU launchers (blackstar_b200/dist.py):
+// the launcher owns the all-to-all between them.
+extern "C" int bsb_bloom_h_device(bsb_ctx *ctx, int radius, int width, int rows, const void *dev_rows, void *dev_midT,
+                                  void *dev_imgT)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    if (radius < 1 || width <= 0 || rows < 0 || (rows > 0 && (!dev_rows || !dev_midT)))
+        return fail(ctx, BSB_ERR_INVALID, "bsb_bloom_h_device: bad argument");
+    return bloom_h_async(ctx, ctx->devs[0], radius, width, rows, static_cast<const float4 *>(dev_rows),
+                         static_cast<float4 *>(dev_midT), static_cast<float4 *>(dev_imgT));
+}
+
+extern "C" int bsb_bloom_v_device(bsb_ctx *ctx, double strength, int radius, int height, int cols, int nseg,
+                                  const void *const *seg_midT, const void *const *seg_imgT, const int *seg_rows,
+                                  void *dev_out_rgba, void *dev_out_rgb8)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    if (radius < 1 || height <= 0 || cols < 0 || !seg_midT || !seg_imgT || !seg_rows || (!dev_out_rgba && !dev_out_rgb8))
+        return fail(ctx, BSB_ERR_INVALID, "bsb_bloom_v_device: bad argument");
+    return bloom_v_async(ctx, ctx->devs[0], strength, radius, height, cols, nseg, reinterpret_cast<const float4 *const *>(seg_midT),
+                         reinterpret_cast<const float4 *const *>(seg_imgT), seg_rows, static_cast<float4 *>(dev_out_rgba),
+                         static_cast<uint8_t *>(dev_out_rgb8));
 }
 
 // ======================================================================== micro-benchmarks

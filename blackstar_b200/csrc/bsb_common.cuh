@@ -115,12 +115,13 @@ struct BoxArgs {
     int n, lines;         // line length, number of lines
     int x_lo, x_hi;       // positions of each line that are written
     float4 *out;          // result of (line l, position x) -> out[(x - x_lo) * out_pitch + l]  (may be null)
-    const float4 *img;    // combine: indexed like out; may alias out
+    const float4 *img;    // combine == 1: indexed like out; may alias out
+    const float4 *seg_img[kMaxSegments];  // combine == 2: the image TRANSPOSED, in pieces laid out like seg_in
     uint8_t *rgb8;        // optional: sRGB8 of the result at rgb8[(x - x_lo) * rgb8_pitch + 3 * l]
     const float *thr;     // 256 floats: sRGB8 thresholds (host_setup.cpp: srgb8_thresholds)
     size_t out_pitch, rgb8_pitch;
     int r;                // box radius (src/ImageFilters.hs:83)
-    int combine;          // out = img + strength * blur (src/ImageFilters.hs:85-86)
+    int combine;          // out = img + strength * blur (src/ImageFilters.hs:85-86); 0 = just the blur
     float norm;           // 1 / (2r+1)   (src/ImageFilters.hs:51)
     float strength;
 };

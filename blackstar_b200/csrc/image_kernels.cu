@@ -75,7 +75,7 @@ __device__ __forceinline__ unsigned srgb8_level(float x, const float *__restrict
 //  * the scan of the chunk totals is a FLOAT warp scan (32 chunks = 32 C pixels: exact to 2e-5 of a
 //    2r-pixel window sum) and FP64 only across the T/32 warp totals.
 template <int C, int T, int DELTA>
-__global__ void __launch_bounds__(T, BSB_BLOOM_CTAS * 512 / T) box3_kernel(const __grid_constant__ BoxArgs A)
+__global__ void __launch_bounds__(T, (BSB_BLOOM_CTAS * 512 / T) > 4 ? 4 : (BSB_BLOOM_CTAS * 512 / T)) box3_kernel(const __grid_constant__ BoxArgs A)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int NW = T / 32;
@@ -166,6 +166,16 @@ __global__ void __launch_bounds__(T, BSB_BLOOM_CTAS * 512 / T) box3_kernel(const
                 base[0] = __shfl_sync(kFullMask, x, (warp + 15) & 15);
                 base[1] = __shfl_sync(kFullMask, x, 16 + ((warp + 15) & 15));
                 base[2] = __shfl_sync(kFullMask, z, (warp + 15) & 15);
+            } else if (NW == 8) {
+                double x = lane < 24 ? WT[lane] : 0.0;           // all three channels: 3 x 8 totals
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const double y = __shfl_up_sync(kFullMask, x, o);
+                    if ((lane & 7) >= o) x += y;
+                }
+                base[0] = __shfl_sync(kFullMask, x, (warp + 7) & 7);
+                base[1] = __shfl_sync(kFullMask, x, 8 + ((warp + 7) & 7));
+                base[2] = __shfl_sync(kFullMask, x, 16 + ((warp + 7) & 7));
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(T, BSB_BLOOM_CTAS * 512 / T) box3_kernel(const
 
     // 32-byte aligned pairs: even pitch and 32-byte aligned buffers
     const bool wide = n_here == 2 && (A.out_pitch & 1) == 0 &&
-                      ((reinterpret_cast<size_t>(A.out) | reinterpret_cast<size_t>(A.img)) & 31) == 0;
+                      ((reinterpret_cast<size_t>(A.out) | (A.combine == 1 ? reinterpret_cast<size_t>(A.img) : 0)) & 31) == 0;
 #pragma unroll
     for (int j = 0; j < C; j++) {
         const int x = x0 + j;
@@ -221,7 +231,13 @@ __global__ void __launch_bounds__(T, BSB_BLOOM_CTAS * 512 / T) box3_kernel(const
         float4 b = make_float4(v[j][0], v[j][1], v[j][2], 1.0f);
         if (A.combine) {
             float4 pa, pb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (wide) ld256(&A.img[o], pa, pb);
+            if (A.combine == 2) {
+                int sg = 0;
+                while (sg + 1 < A.nseg && x >= A.seg_start[sg + 1]) sg++;
+                const float4 *q = A.seg_img[sg] + (size_t)line0 * A.seg_pitch[sg] + (size_t)(x - A.seg_start[sg]);
+                pa = *q;
+                if (n_here == 2) pb = q[A.seg_pitch[sg]];
+            } else if (wide) ld256(&A.img[o], pa, pb);
             else { pa = A.img[o]; if (n_here == 2) pb = A.img[o + 1]; }
             a = make_float4(fmaf(A.strength, a.x, pa.x), fmaf(A.strength, a.y, pa.y), fmaf(A.strength, a.z, pa.z), pa.w);
             b = make_float4(fmaf(A.strength, b.x, pb.x), fmaf(A.strength, b.y, pb.y), fmaf(A.strength, b.z, pb.z), pb.w);
@@ -277,11 +293,41 @@ int bloom_max_line() { return 8 * 1024; }
 cudaError_t launch_box3(const BoxArgs &A, cudaStream_t stream)
 {
     if (A.lines <= 0 || A.n <= 0) return cudaSuccess;
-    const int n = A.n;
-    if (n <= 1024) return launch_box3_ct<2, 512>(A, stream);
+    const int n = A.n;   // every thread of a CTA works whether its pixels are inside the line or not: size it
+    if (n <= 512) return launch_box3_ct<2, 256>(A, stream);
+    if (n <= 1024) return launch_box3_ct<4, 256>(A, stream);
+    if (n <= 2048) return launch_box3_ct<8, 256>(A, stream);
     if (n <= 4096) return launch_box3_ct<8, 512>(A, stream);
     if (n <= 8192) return launch_box3_ct<8, 1024>(A, stream);
     return cudaErrorInvalidValue;
+}
+
+// ---- float4 transpose: in [rows][cols] (pitch in_pitch) -> out [cols][rows] (pitch out_pitch)
+__global__ void __launch_bounds__(256) transpose_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int rows, int cols,
+                                                        size_t in_pitch, size_t out_pitch)
+{
+    __shared__ float4 tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int y = by + ty + k, x = bx + tx;
+        if (y < rows && x < cols) tile[ty + k][tx] = in[(size_t)y * in_pitch + x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int x = bx + ty + k, y = by + tx;
+        if (x < cols && y < rows) out[(size_t)x * out_pitch + y] = tile[tx][ty + k];
+    }
+}
+
+cudaError_t launch_transpose(const float4 *in, float4 *out, int rows, int cols, size_t in_pitch, size_t out_pitch, cudaStream_t stream)
+{
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, stream>>>(in, out, rows, cols, in_pitch, out_pitch);
+    return cudaGetLastError();
 }
 
 // ---- lines longer than the shared-memory kernel takes: the reference's own algorithm, one thread

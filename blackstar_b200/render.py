@@ -137,9 +137,15 @@ class Renderer:
         self._check(self._L.bsb_bloom(self._ctx, float(strength), int(divider), W, H, img.ctypes.data, out.ctypes.data))
         return out
 
-    def bloom_device(self, strength: float, divider: int, W: int, H: int, src_ptr: int, dst_ptr: int):
-        self._check(self._L.bsb_bloom_device(self._ctx, float(strength), int(divider), W, H,
-                                             ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr)))
+    def bloom_device(self, strength: float, divider: int, W: int, H: int, src_ptr: int, dst_ptr: int, rgb8_ptr: int = 0):
+        """ImageFilters.bloom on device memory; with ``rgb8_ptr`` writeImg's sRGB8 map of the result is
+        written too (fused into the second launch), and ``dst_ptr`` may then be 0."""
+        self._check(self._L.bsb_bloom_to_device(self._ctx, float(strength), int(divider), W, H, ctypes.c_void_p(src_ptr),
+                                                ctypes.c_void_p(dst_ptr or None), ctypes.c_void_p(rgb8_ptr or None)))
+
+    def download_2d(self, host_ptr: int, host_pitch: int, dev_ptr: int, dev_pitch: int, width_bytes: int, rows: int):
+        self._check(self._L.bsb_download_2d(self._ctx, ctypes.c_void_p(host_ptr), host_pitch, ctypes.c_void_p(dev_ptr),
+                                            dev_pitch, width_bytes, rows))
 
     # ------------------------------------------------------------------ doRender
     def do_render(self, cfg: Config, out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -166,6 +172,30 @@ class Renderer:
         self.last_stats = st.as_dict()
         self._check(rc)
         return out
+
+    def render_full_device(self, cfg: Config, want_float: bool = True, want_rgb8: bool = False):
+        """doRender with the frame left on the GPU(s) of the ctx; asynchronous (``synchronize``)."""
+        cam, scn = to_c(cfg)
+        self._check(self._L.bsb_render_full_device(self._ctx, ctypes.byref(cam), ctypes.byref(scn), int(want_float), int(want_rgb8)))
+
+    def synchronize(self):
+        self._check(self._L.bsb_synchronize(self._ctx))
+
+    # ------------------------------------------------------------------ distributed bloom (one process per GPU)
+    def bloom_h_device(self, radius: int, W: int, rows: int, src_ptr: int, midT_ptr: int, imgT_ptr: int = 0):
+        """Horizontal half of the bloom on a tile of rows: [rows][W] -> transposed [W][rows]."""
+        self._check(self._L.bsb_bloom_h_device(self._ctx, int(radius), int(W), int(rows), ctypes.c_void_p(src_ptr),
+                                               ctypes.c_void_p(midT_ptr), ctypes.c_void_p(imgT_ptr or None)))
+
+    def bloom_v_device(self, strength: float, radius: int, H: int, cols: int, seg_mid: Sequence[int], seg_img: Sequence[int],
+                       seg_rows: Sequence[int], out_ptr: int = 0, rgb8_ptr: int = 0):
+        """Vertical half + combine (+ sRGB8) on a band of ``cols`` columns assembled from row-tile pieces."""
+        n = len(seg_rows)
+        mids = (ctypes.c_void_p * n)(*[ctypes.c_void_p(p) for p in seg_mid])
+        imgs = (ctypes.c_void_p * n)(*[ctypes.c_void_p(p) for p in seg_img])
+        rows = (ctypes.c_int * n)(*[int(x) for x in seg_rows])
+        self._check(self._L.bsb_bloom_v_device(self._ctx, float(strength), int(radius), int(H), int(cols), n, mids, imgs, rows,
+                                               ctypes.c_void_p(out_ptr or None), ctypes.c_void_p(rgb8_ptr or None)))
 
     def to_srgb8(self, img: np.ndarray) -> np.ndarray:
         """The per-pixel map of writeImg: toWord8 . fmap sRGB  (src/Raytracer.hs:23-32)."""

@@ -35,7 +35,7 @@ extern "C" {
 #define BSB_ERR_INVALID 1   /* bad argument (NULL, negative size, rows out of range ...) */
 #define BSB_ERR_CUDA 2      /* a CUDA runtime call failed */
 #define BSB_ERR_NCCL 3      /* NCCL missing or a NCCL call failed (multi-GPU only) */
-#define BSB_ERR_UNSUPPORTED 4 /* e.g. image wider than the bloom kernel's shared-memory row */
+#define BSB_ERR_UNSUPPORTED 4 /* e.g. multi-GPU bloom of an image side above 8192 */
 #define BSB_ERR_STEPCAP 5   /* a ray hit the step cap (the reference would loop forever) */
 
 typedef struct bsb_ctx bsb_ctx;
@@ -106,7 +106,12 @@ const char *bsb_version(void);
  * NULL restores the ctx's stream; pass cudaStreamLegacy ((void*)1) for the default stream. */
 int bsb_set_stream(bsb_ctx *ctx, void *cuda_stream);
 
-/* Tuning knobs.  "trace_variant" selects the schedule / build of the trace kernel; every variant
+/* Tuning knobs.
+ *   "copy_threads"  host threads that move staged chunks into pageable output buffers (default 4;
+ *                   0 = leave copies into pageable memory to the driver)
+ *   "step_cap"      RK4 steps after which a ray is abandoned (default 1e6; the reference has no cap and
+ *                   would not terminate; a capped ray makes the render return BSB_ERR_STEPCAP)
+ * "trace_variant" selects the schedule / build of the trace kernel; every variant
  * computes the same image bit for bit:
  *   6 (default) one tile of 32 rays per warp, <=128 registers (2 CTAs/SM)
  *   0 / 4       same schedule compiled for 3 / 4 CTAs per SM (80 / 64 registers)
@@ -142,18 +147,52 @@ int bsb_bloom_device(bsb_ctx *ctx, double strength, int divider, int width, int 
                      const void *dev_in_rgba, void *dev_out_rgba);
 
 /* ---- what Main.doRender does between reading the scene and writeImg
- * (app/Main.hs:105-118): render on every GPU of the ctx (row tiles), gather the tiles on
- * the first GPU (one NCCL gather), bloom if bloom_strength != 0, copy to the host. */
+ * (app/Main.hs:105-118): render, bloom if bloom_strength != 0, copy to the host.
+ * On a ctx with N > 1 GPUs: GPU k traces a tile of rows and runs the horizontal half of the bloom
+ * on it; ONE all-to-all over NVLink re-cuts the frame into column bands; GPU k runs the vertical
+ * half + `img + strength * blur` on its band, and the N bands are copied into out_rgba in parallel
+ * (N PCIe links).  out_rgba may be pageable (plain malloc) or page-locked; see "copy_threads". */
 int bsb_render_full(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
                     float *out_rgba, bsb_stats *stats);
+/* Same work, frame left on the GPU(s); asynchronous (bsb_synchronize waits for it). */
+int bsb_render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
+                           int want_float, int want_rgb8);
+int bsb_synchronize(bsb_ctx *ctx);
 
 /* ---- writeImg's pixel map (src/Raytracer.hs:23-32): sRGB then toWord8, RGB8 out ------- */
 int bsb_to_srgb8(bsb_ctx *ctx, int width, int height, const float *in_rgba, uint8_t *out_rgb8);
 int bsb_to_srgb8_device(bsb_ctx *ctx, int width, int height, const void *dev_in_rgba,
                         void *dev_out_rgb8);
-/* render_full + sRGB/8-bit on the device; only width*height*3 bytes cross PCIe. */
+/* doRender + writeImg's map in one call: the sRGB + toWord8 map runs in the epilogue of the last
+ * bloom launch, the float frame is never written, and only width*height*3 bytes cross PCIe.
+ * This is what the reference-side shim calls before its PNG encoder. */
 int bsb_render_full_srgb8(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
                           uint8_t *out_rgb8, bsb_stats *stats);
+/* Both images of one render; either pointer may be NULL. */
+int bsb_render_full_both(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
+                         float *out_rgba, uint8_t *out_rgb8, bsb_stats *stats);
+
+/* bloom with writeImg's map fused: writes the float frame and / or its sRGB8 image (either may be NULL) */
+int bsb_bloom_to_device(bsb_ctx *ctx, double strength, int divider, int width, int height,
+                        const void *dev_in_rgba, void *dev_out_rgba, void *dev_out_rgb8);
+/* rows x width_bytes of dense device rows into a host frame with row pitch host_pitch, ordered after
+ * the work queued on the ctx stream (asynchronous for page-locked memory, staged for pageable). */
+int bsb_download_2d(bsb_ctx *ctx, void *host_dst, size_t host_pitch, const void *dev_src,
+                    size_t dev_pitch, size_t width_bytes, int rows);
+
+/* ---- the two halves of the bloom as separate device-side steps, for launchers that run ONE
+ * PROCESS PER GPU and own the exchange between them (blackstar_b200/dist.py under torchrun):
+ *   h: rows x width tile -> its box^3-filtered rows, TRANSPOSED ([width][rows] float4), and
+ *      optionally the tile itself transposed;  no communication (boxBlur's horizontal sweeps,
+ *      src/ImageFilters.hs:72-73, commute with the vertical ones);
+ *   v: `cols` columns of the full-height frame, each assembled from nseg row-tile pieces
+ *      (piece s of column l = seg_midT[s] + l * seg_rows[s]); writes img + strength * blur for
+ *      the band as [height][cols] float4 and / or its sRGB8 image [height][cols*3]. */
+int bsb_bloom_h_device(bsb_ctx *ctx, int radius, int width, int rows, const void *dev_rows_rgba,
+                       void *dev_midT, void *dev_imgT);
+int bsb_bloom_v_device(bsb_ctx *ctx, double strength, int radius, int height, int cols, int nseg,
+                       const void *const *seg_midT, const void *const *seg_imgT,
+                       const int *seg_rows, void *dev_out_rgba, void *dev_out_rgb8);
 
 /* ---- device micro-benchmarks used for the roofline denominators ------------------------
  * Dependent-free DFMA streams on every SM: returns achieved FP64 TFLOP/s (2 flops/FMA). */

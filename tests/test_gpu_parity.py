@@ -188,6 +188,56 @@ def test_fused_srgb8_epilogue_equals_separate_map(rnd, scenes_dir, stars40k, res
     np.testing.assert_array_equal(rnd.do_render_srgb8(nobloom), po.to_srgb8(rgb(rnd.do_render(nobloom))))
 
 
+@pytest.mark.parametrize("shape,divider,world", [((96, 200), 10, 3), ((1080, 1920), 25, 8), ((130, 70), 4, 2), ((64, 2100), 25, 4)])
+def test_distributed_bloom_building_blocks_on_one_gpu(rnd, shape, divider, world):
+    """bsb_bloom_h_device / bsb_bloom_v_device as the N-rank pipeline uses them, with the all-to-all
+    done by hand on one GPU: row tiles -> H^3 (transposed) -> column bands from row-tile pieces -> V^3 +
+    combine + sRGB8.  Against the oracle, the one-piece bloom of the library and the oracle's 8-bit map."""
+    import torch
+    from blackstar_b200.dist import col_bands, even_row_tiles
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    img = np.ones((H, W, 4), dtype=np.float32)
+    img[..., :3] = rng.uniform(0, 1.1, (H, W, 3)).astype(np.float32)
+    ref = po.bloom(0.35, divider, rgb(img))
+    one = rnd.bloom(0.35, divider, img)
+    r = W // divider
+    tiles, bands = even_row_tiles(H, world), col_bands(W, world)
+    rnd.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        dev = torch.from_numpy(img).cuda()
+        midT, imgT = [], []
+        for r0, r1 in tiles:
+            m = torch.empty((W, r1 - r0, 4), device="cuda")
+            t = torch.empty((W, r1 - r0, 4), device="cuda")
+            rnd.bloom_h_device(r, W, r1 - r0, dev[r0:r1].data_ptr(), m.data_ptr(), t.data_ptr())
+            midT.append(m)
+            imgT.append(t)
+        torch.cuda.synchronize()
+        for (r0, r1), t in zip(tiles, imgT):       # the transposed copy of the tile is exact
+            assert torch.equal(t, dev[r0:r1].permute(1, 0, 2))
+        out = np.zeros((H, W, 4), dtype=np.float32)
+        out8 = np.zeros((H, W, 3), dtype=np.uint8)
+        for c0, c1 in bands:
+            if c1 == c0:
+                continue
+            pm = [m[c0:c1].contiguous() for m in midT]     # what the all-to-all delivers: one piece per source rank
+            pi = [t[c0:c1].contiguous() for t in imgT]
+            band = torch.empty((H, c1 - c0, 4), device="cuda")
+            band8 = torch.empty((H, c1 - c0, 3), device="cuda", dtype=torch.uint8)
+            rnd.bloom_v_device(0.35, r, H, c1 - c0, [x.data_ptr() for x in pm], [x.data_ptr() for x in pi],
+                               [b - a for a, b in tiles], band.data_ptr(), band8.data_ptr())
+            torch.cuda.synchronize()
+            out[:, c0:c1] = band.cpu().numpy()
+            out8[:, c0:c1] = band8.cpu().numpy()
+    finally:
+        rnd.set_stream(None)
+    assert np.abs(rgb(out) - ref).max() < 1e-5
+    assert np.abs(out - one).max() < 2e-6          # same filter, different chunking of the prefix sums
+    assert (out[..., 3] == 1).all()
+    np.testing.assert_array_equal(out8, po.to_srgb8(rgb(out)))
+
+
 def test_bloom_device_in_place_and_unaligned_views(rnd):
     # the device entry point on torch tensors: in place, out of place, and on a view whose base
     # address is only 16-byte aligned (the 256-bit path must not be taken there)
