@@ -3,25 +3,34 @@
 
 Workload (config.workload): scenes/default-aa.yaml at 4096x4096 final resolution: 4x
 supersampling (67.1 M traced rays/frame), synthetic 468 861-star catalogue looked up in the
-k-d tree, bloom (BASELINE.json configs[2], north_star's target scene).  A "step" is one frame:
-trace (row-tiled over the ranks) -> one NCCL gather on rank 0 -> bloom on rank 0.
+k-d tree, bloom (BASELINE.json configs[2], north_star's target scene).  A "step" is one frame =
+Main.doRender between reading the scene and writeImg (app/Main.hs:105-118).
 
-  value : whole-job Mrays/s with everything resident in HBM (star tree uploaded once; frame
-          left in HBM), CUDA events, max over ranks.
-  e2e   : the same frame through the public API with HOST buffers: scene/camera structs
-          in, pinned host framebuffer out (D2H inside the timed region).
+  value : whole-job Mrays/s with everything resident in HBM (star tree uploaded once; the bloomed
+          float frame is left in HBM), CUDA events, max over ranks.
+  e2e   : the same frame through the call the reference-side shim makes, bsb_render_full_srgb8
+          (integration/haskell/RaytracerB200.hs), with a caller-owned plain-malloc host buffer: scene
+          and camera structs in, the RGB8 image writeImg hands to its PNG encoder out, the
+          device->host copy inside the timed region.  `e2e.variants` holds the float frame
+          (bsb_render_full) and page-locked buffers beside it.
+  N > 1 : one process per GPU (torchrun): row tiles -> horizontal bloom per tile -> ONE all-to-all
+          over NVLink into column bands -> vertical bloom per band -> every rank copies its band
+          into a shared, page-locked host frame over its own PCIe link.  Scaling is STRONG (same
+          frame, more GPUs).  `--inlib` (plain python, no torchrun) runs the same pipeline inside ONE
+          process through bsb_create(N) / bsb_render_full*.
   --impl reference : the reference's CPU path.  GHC is not in this image, so this is the C
           port of the reference (oracle/), all host threads, a bounded band of the same frame.
-
-One process per GPU (torchrun) for --gpus > 1; scaling is STRONG (same frame, more GPUs).
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,8 +41,6 @@ if ROOT not in sys.path:
 SCENE = "default-aa.yaml"
 RES = (4096, 4096)
 FLOPS_PER_STEP = 156  # 141 (rk4 as written) + 15 (findColor), sqrt/div = 1 flop
-DP_INSTR_PER_STEP = 61.4  # FP64-pipe instructions the kernel issues per RK4 step (ncu, incl. ray setup)
-OTHER_INSTR_PER_STEP = 19.1  # all other instructions per RK4 step (ncu)
 METRIC = "Mrays/sec on default.yaml at 4096x4096"
 
 
@@ -44,16 +51,18 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--res", type=int, nargs=2, default=list(RES), help="override the frame size (debug only)")
-    ap.add_argument("--variant", type=int, default=None, help="trace schedule 0..3 (default: library default)")
+    ap.add_argument("--scene", default=SCENE, help="override the scene (non-headline lines: tools/bench_c4_c5.py)")
+    ap.add_argument("--variant", type=int, default=None, help="trace schedule 0..4, 6 (default: library default)")
+    ap.add_argument("--inlib", action="store_true", help="ONE process drives all --gpus GPUs through bsb_create(N)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def load_workload(res):
+def load_workload(args):
     from blackstar_b200 import config
-    cfg = config.load_config(os.path.join(ROOT, "scenes", SCENE))
-    return config.with_resolution(cfg, res[0], res[1])
+    cfg = config.load_config(os.path.join(ROOT, "scenes", args.scene))
+    return config.with_resolution(cfg, args.res[0], args.res[1])
 
 
 def measured_peaks():
@@ -64,6 +73,16 @@ def measured_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def trace_kernel_counts():
+    """Per-RK4-step instruction counts and DRAM traffic of the trace kernel, from this round's ncu
+    capture of the headline frame (profiles/trace_kernel_traffic.json, written by tools/ncu_trace_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -182,7 +201,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     from blackstar_b200 import starmap
-    cfg = load_workload(args.res)
+    cfg = load_workload(args)
     arm = CpuArm(cfg, starmap.synthetic_stars())
     total = args.steps + args.warmup
     per_step = max(1.0, min(20.0, 150.0 / max(1, total)))
@@ -198,7 +217,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"scenes/{SCENE} at {args.res[0]}x{args.res[1]} (x4 supersampling, 468861-star "
+        "config": {"workload": f"scenes/{args.scene} at {args.res[0]}x{args.res[1]} (x4 supersampling, 468861-star "
                                "synthetic catalogue); each step = a bounded band of rows of that frame, no bloom",
                    "note": "GHC/stack are not installed here: this is the C port of the reference "
                            "(oracle/, gcc -O2 -ffp-contract=off, pthreads over rows), not the Haskell binary"},
@@ -210,6 +229,66 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------------- NCCL evidence
+def nccl_log_setup(world):
+    """NCCL's own init log is the evidence that the communicator spans `world` ranks.  If the caller's
+    environment already asks for it (NCCL_DEBUG set) it is left exactly as asked.  Otherwise it is turned
+    on INTO A FILE (stdout has to stay one JSON line) and summarised on rank 0 afterwards."""
+    if world <= 1:
+        return None
+    if "BENCH_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+    if os.environ.get("NCCL_DEBUG_FILE"):
+        return os.environ["NCCL_DEBUG_FILE"]          # somebody is already collecting the log: leave it alone
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE"):
+        return None                                   # asked for on the console: leave it alone
+    d = os.environ.get("BENCH_NCCL_LOG_DIR") or tempfile.gettempdir()
+    path = os.path.join(d, f"bsb_nccl_{os.environ.get('MASTER_PORT', '0')}_%h_%p.log")
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+    os.environ["NCCL_DEBUG_FILE"] = path
+    return path
+
+
+def nccl_log_summary(pattern, world):
+    if not pattern:
+        return None
+    files = glob.glob(re.sub(r"%[hp]", "*", pattern))
+    nranks, version, lines = set(), None, []
+    for f in files:
+        try:
+            for ln in open(f, errors="replace"):
+                m = re.search(r"nranks (\d+)", ln)
+                if m and ("Init COMPLETE" in ln or "ncclCommInitRank" in ln or "comm 0x" in ln):
+                    nranks.add(int(m.group(1)))
+                    if "Init COMPLETE" in ln:
+                        lines.append(ln.strip())
+                m = re.search(r"NCCL version ([0-9.]+\S*)", ln)
+                if m:
+                    version = m.group(1)
+        except Exception:
+            continue
+    for ln in lines[:world]:
+        print(ln, file=sys.stderr)
+    return {"nranks_seen": sorted(nranks), "nranks_ok": world in nranks if nranks else None, "version": version,
+            "log_files": len(files)}
+
+
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when a communicator is created; stdout owes ONE JSON
+    line, so file descriptor 1 points at stderr while communicators are being set up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import numpy as np
@@ -217,188 +296,244 @@ def run_b200(args):
     import torch.distributed as dist
 
     from blackstar_b200 import starmap
-    from blackstar_b200.dist import TiledFrame
+    from blackstar_b200.dist import DistributedFrame
     from blackstar_b200.render import Renderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus != world:
+    if args.inlib and world > 1:
+        raise SystemExit("--inlib is the one-process arm: run it with plain python, not under torchrun")
+    if args.gpus != world and not args.inlib:
         if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU), or with --inlib")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: blackstar_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    nccl_log = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if "BENCH_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout; we owe ONE JSON line
-        dist.init_process_group("nccl", device_id=device)
+        nccl_log = nccl_log_setup(world)
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+    n_gpus = args.gpus if args.inlib else world
 
-    cfg = load_workload(args.res)
+    cfg = load_workload(args)
     W, H = cfg.scene.resolution
     ss = 4 if cfg.scene.supersampling else 1
     rays_per_frame = W * H * ss
     stars = starmap.synthetic_stars()  # N = 468 861, seed 20190412
 
-    r = Renderer(devices=[local])
+    with stdout_to_stderr():
+        r = Renderer(n_gpus=n_gpus) if args.inlib and n_gpus > 1 else Renderer(devices=[local])
     r.set_stars(stars)
     if args.variant is not None:
         r.set_option("trace_variant", args.variant)
-    frame = TiledFrame(r, cfg, rank, world, device)
+    multi_proc = world > 1
+    frame = None
+    if multi_proc:
+        frame = DistributedFrame(r, cfg, rank, world, device)
+    elif not (args.inlib and n_gpus > 1):
+        r.set_stream(torch.cuda.current_stream(device).cuda_stream)   # so torch's events bracket the library's work
 
     def barrier():
-        if world > 1:
+        if multi_proc:
             dist.barrier()
+        if args.inlib:
+            r.synchronize()
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if world == 1:
+        if not multi_proc:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def sum_over_ranks(x: float) -> float:
-        if world == 1:
+        if not multi_proc:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def device_step():
+        if multi_proc:
+            frame.step(want_float=True)
+        else:
+            r.render_full_device(cfg, want_float=True, want_rgb8=False)
+
+    single_launches = 2 + (2 if cfg.scene.bloomStrength != 0 else 0)     # ray tables, trace, bloom x2
+    inlib_launches = n_gpus * (5 if cfg.scene.bloomStrength != 0 else 2)  # + horizontal bloom, transpose, vertical bloom
+
     # ---------------- value: device-resident, K frames back to back
-    frame.calibrate()            # N > 1: adaptive row tiles (untimed, like the warm-up)
+    if multi_proc:
+        frame.calibrate()            # adaptive row tiles (untimed, like the warm-up)
+    elif args.inlib and n_gpus > 1:
+        host_cal = np.empty((H, W, 3), dtype=np.uint8)
+        for _ in range(3):
+            r.do_render_srgb8(cfg, out=host_cal)   # the library re-cuts its row tiles from the measured rates
     for _ in range(args.warmup):
-        frame.step()
+        device_step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    frame.launches = 0
+    if multi_proc:
+        frame.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        frame.step()
+        device_step()
     e1.record()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    # one process driving N GPUs: torch's events only see device 0's default stream -> wall clock between the barriers
+    ms_total = wall_ms if (args.inlib and n_gpus > 1) else max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    launches = int(sum_over_ranks(float(frame.launches)))
+    if multi_proc:
+        launches = int(sum_over_ranks(float(frame.launches)))
+    else:
+        launches = args.steps * (inlib_launches if (args.inlib and n_gpus > 1) else single_launches)
     ms_per_step = ms_total / args.steps
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
     # ---------------- dominant kernel (geodesic trace): live CUDA-event duration per launch
-    trace_ms, steps_total, hits_total = [], 0, 0
-    for _ in range(3):
-        st = frame.step(want_stats=True)
-        trace_ms.append(st["trace_ms"])
-        steps_total, hits_total = st["steps"], st["star_hits"]
+    trace_ms, my_steps = [], 0
+    if multi_proc:
+        my_rows = frame.tiles[rank][1] - frame.tiles[rank][0]
+        for _ in range(3):
+            st = frame.step(want_stats=True)
+            trace_ms.append(st["trace_ms"])
+            my_steps = st["steps"]
+    else:
+        my_rows = H
+        tmp = torch.empty((H, W, 4), dtype=torch.float32, device=device)
+        with Renderer(devices=[local]) as r1:        # the trace kernel of one GPU over the whole frame
+            r1.set_stars(stars)
+            if args.variant is not None:
+                r1.set_option("trace_variant", args.variant)
+            r1.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            for _ in range(3):
+                st = r1.render_device(cfg, tmp.data_ptr(), 0, H, want_stats=True)
+                trace_ms.append(st["trace_ms"])
+                my_steps = st["steps"]
+            # bloom kernels, timed alone
+            bloom_ms = None
+            if cfg.scene.bloomStrength != 0:
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                scratch = torch.empty_like(tmp)
+                reps = 10
+                r1.bloom_device(cfg.scene.bloomStrength, cfg.scene.bloomDivider, W, H, tmp.data_ptr(), scratch.data_ptr())
+                torch.cuda.synchronize()
+                b0.record()
+                for _ in range(reps):
+                    r1.bloom_device(cfg.scene.bloomStrength, cfg.scene.bloomDivider, W, H, tmp.data_ptr(), scratch.data_ptr())
+                b1.record()
+                torch.cuda.synchronize()
+                bloom_ms = b0.elapsed_time(b1) / reps
+                del scratch
+            fp64_peak = r1.measure_fp64_peak()
+        del tmp
     barrier()
-    k1_ms = sum(trace_ms) / len(trace_ms)              # rank 0's own launch (its tile)
-    rk4_steps = int(sum_over_ranks(float(steps_total)))
-    my_rows = frame.tiles[rank][1] - frame.tiles[rank][0]
-    my_steps = steps_total
+    k1_ms = sum(trace_ms) / len(trace_ms)              # this rank's own launch (its tile)
+    rk4_steps = int(sum_over_ranks(float(my_steps)))
+    if multi_proc:
+        fp64_peak = r.measure_fp64_peak() if rank == 0 else 0.0
+        bloom_ms = None
     k1_bytes = 16.0 * my_rows * W                      # one float4 store per OUTPUT pixel
     peaks, peak_kind = measured_peaks()
-    fp64_peak = r.measure_fp64_peak() if rank == 0 else 0.0
-    # bloom kernels, timed alone on rank 0
-    bloom_ms = None
-    if rank == 0 and cfg.scene.bloomStrength != 0:
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        scratch = torch.empty_like(frame.full)
-        scratch.copy_(frame.full)
-        torch.cuda.synchronize()
-        reps = 5
-        b0.record()
-        for _ in range(reps):
-            r.bloom_device(cfg.scene.bloomStrength, cfg.scene.bloomDivider, W, H, frame.full.data_ptr(), scratch.data_ptr())
-        b1.record()
-        torch.cuda.synchronize()
-        bloom_ms = b0.elapsed_time(b1) / reps
-        del scratch
 
-    # ---------------- e2e: public API, host buffers, D2H inside the timed region
-    # (a) synchronous: every frame is traced, gathered, bloomed and copied to pinned host memory
-    #     before the next one starts -- the headline e2e;
-    # (b) pipelined: same work, but the copy of frame i runs on a copy stream while frame i+1 is
-    #     traced (double-buffered frames) -- what a batch / animation driver gets.
-    host = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else None
-    for _ in range(max(1, min(2, args.warmup))):
-        frame.step_to_host(host[0] if rank == 0 else None)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        frame.step_to_host(host[0] if rank == 0 else None)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    # ---------------- e2e: the reference-facing call, HOST buffers, D2H inside the timed region
+    def timed_host(fn):
+        for _ in range(max(1, min(2, args.warmup))):
+            fn()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t) * 1e3) / args.steps
+
+    variants = {}
+    if multi_proc:
+        ms8 = timed_host(lambda: frame.step_to_host(rgb8=True))
+        ms32 = timed_host(lambda: frame.step_to_host(rgb8=False))
+        variants["srgb8_shared_pinned"] = ms8
+        variants["f32_shared_pinned"] = ms32
+        e2e_ms = ms8
+        e2e_path = ("blackstar_b200.dist.DistributedFrame.step_to_host(rgb8=True): bsb_render_device + bsb_bloom_h_device + "
+                    "all-to-all + bsb_bloom_v_device + bsb_download_2d into a shared page-locked host frame, one rank per GPU")
+    else:
+        pin8 = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy()
+        pin32 = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True).numpy()
+        pag8 = np.zeros((H, W, 3), dtype=np.uint8)        # plain malloc, pages touched (what a reused caller buffer is)
+        pag32 = np.zeros((H, W, 4), dtype=np.float32)
+        variants["srgb8_pageable"] = timed_host(lambda: r.do_render_srgb8(cfg, out=pag8))
+        variants["srgb8_pinned"] = timed_host(lambda: r.do_render_srgb8(cfg, out=pin8))
+        variants["f32_pageable"] = timed_host(lambda: r.do_render(cfg, out=pag32))
+        variants["f32_pinned"] = timed_host(lambda: r.do_render(cfg, out=pin32))
+        e2e_ms = variants["srgb8_pageable"]
+        e2e_path = ("bsb_render_full_srgb8 into a caller-owned plain-malloc buffer (what integration/haskell/RaytracerB200.hs "
+                    "passes)" + (f", one process driving {n_gpus} GPUs" if n_gpus > 1 else ""))
+        del pin8, pin32, pag8, pag32
     e2e_value = rays_per_frame / (e2e_ms * 1e-3) / 1e6
-    # (c) the image writeImg consumes: sRGB + 8 bit on the device, 3 bytes per pixel over PCIe
-    host8 = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
-    frame.step_to_host_srgb8(host8)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        frame.step_to_host_srgb8(host8)
-    e1.record()
-    barrier()
-    e2e8_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    e2e8_value = rays_per_frame / (e2e8_ms * 1e-3) / 1e6
-    frame.enable_double_buffering()
-    for _ in range(2):
-        frame.step_to_host_pipelined(host)
-    frame.drain()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        frame.step_to_host_pipelined(host)
-    frame.drain()
-    e1.record()
-    barrier()
-    e2e_pipe_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    e2e_pipe_value = rays_per_frame / (e2e_pipe_ms * 1e-3) / 1e6
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         arm = CpuArm(cfg, stars)
         v, desc, _, _ = arm.sample(args.cpu_seconds)
         cpu = {"value": v, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
                "sample": desc + "; C port of the reference (GHC unavailable), all host threads"}
 
+    tiles = frame.tiles if multi_proc else [[0, H]]
+    bands = frame.bands if multi_proc else [[0, W]]
+    if multi_proc:
+        frame.close()
+    r.close()
+    nccl = None
+    if multi_proc:
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank == 0:
+            nccl = nccl_log_summary(nccl_log, world)
+
     if rank == 0:
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        counts = trace_kernel_counts()
+        traffic = counts.get("dram_bytes_per_launch")
+        dp_per_step, other_per_step = counts.get("fp64_instr_per_rk4_step"), counts.get("other_instr_per_rk4_step")
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
         k1_tflops = FLOPS_PER_STEP * my_steps / (k1_ms * 1e-3) / 1e12
+        if n_gpus == 1:
+            par = "one GPU: trace, two bloom launches (sRGB8 fused into the second)"
+        else:
+            par = (f"row tiles over {n_gpus} GPUs -> horizontal bloom per tile -> one NCCL all-to-all into column bands -> "
+                   "vertical bloom + combine per band; the finished frame is a set of column bands (HBM) / assembled in host "
+                   "memory by N parallel D2H copies" + ("; ONE process (bsb_create(N))" if args.inlib else "; one process per GPU"))
+        d2h = W * H * 3
         line = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"scenes/{SCENE} at {W}x{H}: x4 supersampling ({rays_per_frame} rays/frame), "
+            "config": {"workload": f"scenes/{args.scene} at {W}x{H}: x{ss} supersampling ({rays_per_frame} rays/frame), "
                                    "468861-star synthetic catalogue (seed 20190412) in the k-d tree, bloom",
-                       "parallelism": f"row tiles over {world} GPU(s), one NCCL gather to rank 0, bloom on rank 0",
-                       "tiles": [list(t) for t in frame.tiles],
+                       "parallelism": par, "tiles": [list(t) for t in tiles], "bands": [list(b) for b in bands],
                        "l2": "each step writes a 268 MB frame (> 126 MB L2); the 22 MB star tree is L2-resident by design",
-                       "trace_variant": args.variant},
+                       "trace_variant": args.variant, "inlib": bool(args.inlib)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 176, "d2h_bytes_per_step": W * H * 16,
-                    "pipelined": {"value": e2e_pipe_value, "ms_per_step": e2e_pipe_ms,
-                                  "note": "same bytes; D2H of frame i overlaps the trace of frame i+1"},
-                    "srgb8": {"value": e2e8_value, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": W * H * 3,
-                              "note": "synchronous; sRGB + 8-bit map (writeImg, src/Raytracer.hs:23-32) on the "
-                                      "device, the RGB8 image is what crosses PCIe"}},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "path": e2e_path,
+                    "h2d_bytes_per_step": 176, "d2h_bytes_per_step": d2h,
+                    "variants_ms_per_step": variants,
+                    "variants_mrays_per_s": {k: rays_per_frame / (v * 1e-3) / 1e6 for k, v in variants.items()},
+                    "note": "srgb8 = the RGB8 image writeImg encodes (3 B/px over PCIe); f32 = the linear float frame of "
+                            "bsb_render_full (16 B/px); pageable = plain malloc (library-staged, multi-threaded copy), "
+                            "pinned = page-locked; wall clock between barrier + synchronize on both sides"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "trace (geodesic RK4 + sky lookup + 2x2 supersample)",
                          "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
@@ -408,30 +543,29 @@ def run_b200(args):
             "roofline_fp64": {"bound": "fp64", "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": (k1_tflops / fp64_peak) if fp64_peak else None,
                               "flops_per_rk4_step": FLOPS_PER_STEP, "rk4_steps_per_frame": rk4_steps,
-                              "peak_kind": "sustained DFMA micro-benchmark measured in this run (2 flops per FMA); "
-                                           "1 ms bursts reach 36.6 (profiles/r01_fp64_pipe_probe.txt)",
-                              "executed": {"dp_instr_per_rk4_step": DP_INSTR_PER_STEP,
-                                           "pipe_frac": (DP_INSTR_PER_STEP * my_steps / (k1_ms * 1e-3)) / (fp64_peak * 1e12 / 2)
-                                           if fp64_peak else None,
-                                           "note": "the kernel executes 61.4 FP64 (+19.1 other) instructions per RK4 step (ncu, "
-                                                   "profiles/r01_ncu_summary.json) where the reference as written "
-                                                   "needs 156 flops, so the algorithmic frac can exceed 1; pipe_frac "
-                                                   "is executed FP64 instructions / DFMA issue peak; an FP64 "
-                                                   "instruction holds the issue port 2 cycles, any other 1, and "
-                                                   "2*fp64+others reproduces the measured cycles to 3% (profiles/README.md)"}},
+                              "peak_kind": "sustained DFMA micro-benchmark measured in this run (2 flops per FMA)",
+                              "executed": {"dp_instr_per_rk4_step": dp_per_step, "other_instr_per_rk4_step": other_per_step,
+                                           "source": counts.get("capture"),
+                                           "pipe_frac": (dp_per_step * my_steps / (k1_ms * 1e-3)) / (fp64_peak * 1e12 / 2)
+                                           if (fp64_peak and dp_per_step) else None,
+                                           "note": "instructions the kernel executes per RK4 step, counted by ncu on this round's "
+                                                   "kernel (profiles/trace_kernel_traffic.json); the reference as written needs 156 "
+                                                   "flops per step, so the algorithmic frac exceeds 1; pipe_frac = executed FP64 "
+                                                   "instructions / DFMA issue peak; an FP64 instruction holds the issue port 2 cycles, "
+                                                   "any other 1 (profiles/README.md)"}},
             "cpu_baseline": cpu,
         }
+        if nccl is not None:
+            line["nccl"] = nccl
         if bloom_ms:
             bb = 2.0 * W * H * 16
-            line["roofline_bloom"] = {"bound": "hbm", "kernel": "box3_transpose x2 (bloom)", "achieved": bb / (bloom_ms * 1e-3) / 1e9,
+            line["roofline_bloom"] = {"bound": "hbm", "kernel": "box3_kernel x2 (bloom)", "achieved": bb / (bloom_ms * 1e-3) / 1e9,
                                       "peak": hbm_peak, "unit": "GB/s", "frac": bb / (bloom_ms * 1e-3) / 1e9 / hbm_peak,
                                       "launch_ms": bloom_ms, "moved_bytes": 5.0 * W * H * 16,
-                                      "note": "algorithmic bytes = read + write the frame once; the two-launch "
-                                              "separable implementation moves 2.5x that"}
-        print(json.dumps(line))
-    r.close()
-    if world > 1:
-        dist.destroy_process_group()
+                                      "note": "algorithmic bytes = read + write the frame once; the two-launch separable "
+                                              "implementation moves 2.5x that; bound by L1TEX wavefronts, not DRAM (profiles/)"}
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     return 0
 
 

@@ -193,7 +193,7 @@ struct bsb_ctx {
     std::vector<ncclComm_t> comms;
     std::unique_ptr<CopyPool> pool;   // created on the first copy into pageable memory
     uint8_t *h_stage = nullptr;       // kStageSlots pinned (portable) chunks for copies into pageable memory
-    int copy_threads = 4;
+    int copy_threads = 8;
     uint32_t step_cap = 0;            // 0 = the default of make_frame_params
 };
 

@@ -107,7 +107,7 @@ const char *bsb_version(void);
 int bsb_set_stream(bsb_ctx *ctx, void *cuda_stream);
 
 /* Tuning knobs.
- *   "copy_threads"  host threads that move staged chunks into pageable output buffers (default 4;
+ *   "copy_threads"  host threads that move staged chunks into pageable output buffers (default 8;
  *                   0 = leave copies into pageable memory to the driver)
  *   "step_cap"      RK4 steps after which a ray is abandoned (default 1e6; the reference has no cap and
  *                   would not terminate; a capped ray makes the render return BSB_ERR_STEPCAP)
