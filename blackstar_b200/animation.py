@@ -85,18 +85,28 @@ def interpolate(frames: Sequence[Keyframe], t: float) -> Camera:
                   upVec=_lerp(tp, c1.upVec, c2.upVec), fov=_lerp(tp, c1.fov, c2.fov))
 
 
+def _check_n_frames(n_frames: int):
+    # the reference divides by (nFrames - 1) and produces Infinity / NaN cameras for nFrames = 1
+    # without complaint (src/Animation.hs:62-66); an explicit error is more useful than a NaN scene
+    if n_frames < 2:
+        raise ValueError("nFrames must be at least 2 (the reference interpolates over nFrames - 1 intervals)")
+
+
 def generate_frames(anim: Animation) -> List[Config]:
     """src/Animation.hs:45-52: nFrames points i / (nFrames - 1), keyframes sorted by time (stable)."""
+    _check_n_frames(anim.nFrames)
     stepsize = 1.0 / (anim.nFrames - 1)
     frames = sorted(anim.keyframes, key=lambda k: k.time)
     return [Config(scene=anim.scene, camera=interpolate(frames, i * stepsize)) for i in range(anim.nFrames)]
 
 
 def pad_zero(max_val: int, val: int) -> str:
-    """Util.padZero (src/Util.hs:43-48), including its quirk: nDigits 0 = floor(log10 0) + 1
-    underflows, the zero count goes negative and frame 0 is written WITHOUT padding."""
+    """Util.padZero (src/Util.hs:43-48), including its quirks: nDigits 0 = floor(logBase 10 0) + 1
+    underflows, the zero count goes negative and frame 0 is written WITHOUT padding; and GHC's
+    ``logBase 10 x = log x / log 10`` is 2.9999999999999996 for 1000 (and short for 1e6, 1e9, ...), so
+    such a value counts one digit less than it has (frame 1000 of 1001+ is named ``_01000``)."""
     def n_digits(x: int) -> int:
-        return math.floor(math.log10(x)) + 1
+        return math.floor(math.log(float(x)) / math.log(10.0)) + 1
     if val <= 0 or max_val <= 0:
         return str(val)
     return "0" * max(0, n_digits(max_val) - n_digits(val)) + str(val)

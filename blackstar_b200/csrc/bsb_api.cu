@@ -629,6 +629,10 @@ extern "C" int bsb_set_stars(bsb_ctx *ctx, const bsb_star *stars, size_t n)
     if (!ctx) return BSB_ERR_INVALID;
     if (n > 0 && !stars) return fail(ctx, BSB_ERR_INVALID, "bsb_set_stars: NULL star list");
     if (n > (size_t)1 << 28) return fail(ctx, BSB_ERR_INVALID, "bsb_set_stars: too many stars");
+    if (n > 0) {
+        const std::string bad = validate_stars(stars, n);
+        if (!bad.empty()) return fail(ctx, BSB_ERR_INVALID, "bsb_set_stars: " + bad);
+    }
     HostStarTree t;
     if (n > 0) build_star_tree(stars, n, t);
     for (DeviceState &d : ctx->devs) {

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 
@@ -279,13 +280,30 @@ void spectral_colour(int ch, double &hue, double &sat)
 bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err)
 {
     if (len < 28) { err = "too few bytes"; return false; }  // cereal's message for a failed `skip 28`
-    const size_t n = (len - 28) / 28;                       // :48-49 remaining `div` 28
+    // readMap itself silently drops a ragged tail (:48-49 remaining `div` 28); a catalogue written in
+    // this layout never has one, and a file in another format (e.g. the reference's cereal-encoded
+    // stars.kdt) almost always does -- refuse it instead of rendering noise
+    if ((len - 28) % 28 != 0) {
+        err = "not a PPM-format star catalogue (28-byte header + 28-byte records); note that this library reads "
+              "the catalogue itself, not the stars.kdt tree file generate-tree writes";
+        return false;
+    }
+    const size_t n = (len - 28) / 28;
     out.resize(n);
     const uint8_t *p = bytes + 28;
     for (size_t k = 0; k < n; k++, p += 28) {
         const double ra = f64be(p), dec = f64be(p + 8);      // :50-51
         const int spectral = p[16];                          // :52, then skip 1
         const int16_t mag = (int16_t)(uint16_t(p[18]) << 8 | p[19]);  // :54, then skip 8
+        // right ascension / declination are angles: anything non-finite or far outside [-2pi, 2pi] is
+        // not a catalogue record (random bytes decode to 1e+-300 or NaN)
+        if (!std::isfinite(ra) || !std::isfinite(dec) || std::fabs(ra) > 7.0 || std::fabs(dec) > 7.0) {
+            char buf[160];
+            std::snprintf(buf, sizeof buf, "record %zu is not a star (RA %g, Dec %g): not a PPM-format catalogue", k, ra, dec);
+            err = buf;
+            out.clear();
+            return false;
+        }
         bsb_star &s = out[k];
         s.pos[0] = std::cos(dec) * std::cos(ra);             // :74-75 raDecToCartesian
         s.pos[1] = std::cos(dec) * std::sin(ra);
@@ -295,6 +313,26 @@ bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std
         spectral_colour(spectral, s.hue, s.sat);
     }
     return true;
+}
+
+// The star list handed to bsb_set_stars: unit vectors, finite colours, hue in [0, 1) (massiv-io's
+// toPixelRGB raises `error` outside it).  NaNs would also break the strict weak ordering nth_element needs.
+std::string validate_stars(const bsb_star *stars, size_t n)
+{
+    for (size_t k = 0; k < n; k++) {
+        const bsb_star &s = stars[k];
+        const double q = s.pos[0] * s.pos[0] + s.pos[1] * s.pos[1] + s.pos[2] * s.pos[2];
+        char buf[160];
+        if (!std::isfinite(q) || std::fabs(q - 1.0) > 1e-6) {
+            std::snprintf(buf, sizeof buf, "star %zu: position is not a unit vector (|p|^2 = %g)", k, q);
+            return buf;
+        }
+        if (!std::isfinite(s.hue) || !std::isfinite(s.sat) || s.hue < 0.0 || !(s.hue < 1.0)) {
+            std::snprintf(buf, sizeof buf, "star %zu: hue %g / saturation %g outside the HSI domain (hue in [0,1))", k, s.hue, s.sat);
+            return buf;
+        }
+    }
+    return "";
 }
 
 }  // namespace bsb

@@ -32,6 +32,9 @@ void build_star_tree(const bsb_star *stars, size_t n, HostStarTree &out);
 // StarMap.readMap + starColor' : PPM binary catalogue -> flat star list.
 bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err);
 
+// "" if every star is a finite unit vector with a colour inside the HSI domain, else what is wrong
+std::string validate_stars(const bsb_star *stars, size_t n);
+
 // massiv-io HSI -> RGB on the host (disk colour, once per frame; src/Raytracer.hs:65)
 void host_hsi_to_rgb(double h, double s, double i, double rgb[3]);
 void hue_coefficients(double hue, double k[3]);

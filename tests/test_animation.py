@@ -57,6 +57,13 @@ def test_pad_zero_and_its_quirk():
     assert animation.pad_zero(374, 7) == "007" and animation.pad_zero(374, 42) == "042"
     assert animation.pad_zero(374, 374) == "374" and animation.pad_zero(9, 3) == "3"
     assert animation.pad_zero(374, 0) == "0"          # the reference does not pad frame 0 (src/Util.hs:45)
+    # logBase 10 1000 = log 1000 / log 10 = 2.9999999999999996 in GHC: 1000 counts as a 3-digit number
+    assert animation.pad_zero(1500, 1000) == "01000" and animation.pad_zero(1500, 999) == "0999"
+    assert animation.pad_zero(1000, 7) == "007"       # ... also as the maximum
+    with pytest.raises(ValueError):
+        a = animation.load_animation(ANI)
+        a.nFrames = 1
+        animation.generate_frames(a)
     assert animation.frame_filename("default-ani", 375, 1) == "default-ani_001.yaml"
 
 
