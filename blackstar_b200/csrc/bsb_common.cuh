@@ -38,7 +38,9 @@ static_assert(sizeof(StarRec) == 64, "StarRec is 64 bytes");
 //   Split planes of an implicit complete binary tree; node (d, i) = i-th node of depth d,
 //   children (d+1, 2i) and (d+1, 2i+1); points with coord <= split go left, >= split go right.
 //   Levels 0 .. top_levels-1: `top`, heap order, FLOAT with the split axis in the two lowest
-//     mantissa bits -- 2^13 - 1 nodes = 32 KB, staged in shared memory by every CTA.
+//     mantissa bits -- 2^13 - 1 nodes = 32 KB, staged in shared memory by every CTA.  On these
+//     levels the axis cycles with the level (x, y, z, x, ... as kdt's own build does), so a walk from
+//     the root is a fully unrolled chain of 13 {load, subtract, compare} steps with no decode.
 //   Deeper levels in groups of three: one 64-byte record per 3-level subtree (local heap order
 //     1..7, doubles with the axis in the two lowest mantissa bits), so that three levels cost ONE
 //     dependent L2 access instead of three.  Group g starts at record rec_off[g].

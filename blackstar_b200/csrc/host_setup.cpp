@@ -193,7 +193,7 @@ struct Builder {
             }
             return;
         }
-        int axis = 0;
+        int axis = d < T ? d % 3 : 0;
         double sv = 0.0;
         size_t mid = lo;
         if (hi > lo) {
@@ -207,6 +207,7 @@ struct Builder {
             const double ex[3] = { mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2] };
             axis = (ex[1] > ex[0]) ? 1 : 0;
             if (ex[2] > ex[axis]) axis = 2;
+            if (d < T) axis = d % 3;   // shared-memory levels: the axis is a function of the level (see below)
             mid = lo + (hi - lo) / 2;
             const bsb_star *sp = s;
             const int ax = axis;

@@ -160,8 +160,19 @@ BSB_HD void ray_direction(const FrameParams &P, int x, int y, double dir[3])
     }
 }
 
-// a^(-1/5) to ~2 ulp: single-precision seed, three Newton steps y <- y (1.2 - 0.2 a y^5)
-// (no division; error 3 d^2 per step).  Replaces pow(a, 0.2) in the per-ray set-up.
+// x^(-1/2) for the per-ray frame (device: MUFU seed + Newton, no division; host: 1 / sqrt)
+BSB_HD double inv_sqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / std::sqrt(x);
+#endif
+}
+
+// a^(-1/5) to ~2 ulp: single-precision seed (relative error d ~ 1e-6), two Newton steps
+// y <- y (1.2 - 0.2 a y^5) (no division; error 3 d^2 per step: 3e-12, then 3e-23).  Replaces
+// pow(a, 0.2) in the per-ray set-up.
 BSB_HD double inv_fifth_root(double a)
 {
 #if defined(__CUDA_ARCH__)
@@ -170,7 +181,7 @@ BSB_HD double inv_fifth_root(double a)
     double y = (double)std::pow((float)a, -0.2f);
 #endif
 #pragma unroll
-    for (int it = 0; it < 3; it++) {
+    for (int it = 0; it < 2; it++) {
         const double y2 = y * y;
         const double y5 = (y2 * y2) * y;
         y = y * fma_(-0.2 * a, y5, 1.2);
@@ -233,7 +244,7 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
         F.f1[0] = P.e1[0]; F.f1[1] = P.e1[1]; F.f1[2] = P.e1[2];
         double w0, w1, w2;
         if (!radial) {  // f2 = nhat x f1
-            const double in = 1.0 / sqrt(h2);
+            const double in = inv_sqrt(h2);
             w0 = (n1 * P.e1[2] - n2 * P.e1[1]) * in;
             w1 = (n2 * P.e1[0] - n0 * P.e1[2]) * in;
             w2 = (n0 * P.e1[1] - n1 * P.e1[0]) * in;
@@ -244,18 +255,18 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
             const double d = t0 * P.e1[0] + t1 * P.e1[1] + t2 * P.e1[2];
             w0 = t0 - d * P.e1[0]; w1 = t1 - d * P.e1[1]; w2 = t2 - d * P.e1[2];
         }
-        const double iw = 1.0 / sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+        const double iw = inv_sqrt(w0 * w0 + w1 * w1 + w2 * w2);
         F.f2[0] = w0 * iw; F.f2[1] = w1 * iw; F.f2[2] = w2 * iw;
         F.ysign = !radial ? 0 : ((P.e1[1] > 0.0) - (P.e1[1] < 0.0));
         return;
     }
     // general case: f2 along the line of nodes (n x yhat), f1 = nhat x f2; then f1y = -s/|n| < 0
-    const double in = 1.0 / sqrt(h2);
+    const double in = inv_sqrt(h2);
     const double nh0 = n0 * in, nh1 = n1 * in, nh2 = n2 * in;
     double g0 = -n2, g1 = 0.0, g2 = n0;
     const double dp = g0 * nh0 + g2 * nh2;                 // re-orthogonalise against nhat
     g0 -= dp * nh0; g1 -= dp * nh1; g2 -= dp * nh2;
-    const double ig = 1.0 / sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+    const double ig = inv_sqrt(g0 * g0 + g1 * g1 + g2 * g2);
     g0 *= ig; g1 *= ig; g2 *= ig;
     F.f2[0] = g0; F.f2[1] = g1; F.f2[2] = g2;
     F.f1[0] = nh1 * g2 - nh2 * g1;
@@ -485,7 +496,26 @@ BSB_HD uint32_t star_lookup(const FrameParams &P, const float *top, const double
     uint32_t i = 0;
     for (;;) {
         // ---- shared-memory levels: heap index n = 2^d - 1 + i
-        if (d < TL) {
+        if (d == 0 && TL > 0) {
+            // a walk from the root: the axis of level l is l mod 3 (build_star_tree), so the chain is
+            // unrolled with the query component known at compile time
+            uint32_t n = 0;
+#pragma unroll
+            for (int l = 0; l < kSmemTreeLevels; l++) {
+                if (l < TL) {
+                    const float qa = (l % 3 == 0) ? f0 : ((l % 3 == 1) ? f1 : f2);
+                    const float diff = qa - top[n];
+                    const uint32_t right = diff > 0.0f ? 1u : 0u;
+                    if (fabsf(diff) <= fmargin) {
+                        const uint32_t far = 2u * n + 2u - right;                 // heap index of the other child
+                        stack[sp++] = ((uint32_t)(l + 1) << 26) | (far - ((2u << l) - 1u));
+                    }
+                    n = 2u * n + 1u + right;
+                }
+            }
+            d = TL;
+            i = n - ((1u << TL) - 1u);
+        } else if (d < TL) {
             uint32_t n = (1u << d) - 1u + i;
             const uint32_t n_top = (1u << TL) - 1u;
             do {
