@@ -77,6 +77,7 @@ struct FrameParams {
     double hhh;               // h*(h/2)
     double hsq6;              // h*h/6
     double h3;                // h/3
+    double k13, k23;          // 1/3, 2/3: the step constants in the kernel's units (time in half steps)
     double k14;               // 1.4 (the constant of the |pos|^-5 correction; an FP64 immediate carries
                               // only a high word, so it lives in the constant bank / a register)
     // termination / disk: src/Raytracer.hs:58-65, 88-111

@@ -121,6 +121,8 @@ std::string make_frame_params(const bsb_camera &cam, const bsb_scene &scn, int r
     P.hsq6 = h * h / 6;
     P.h3 = h / 3;
     P.k14 = 1.4;
+    P.k13 = 1.0 / 3.0;
+    P.k23 = 2.0 / 3.0;
     // src/Raytracer.hs:59-62
     const double twoq = 2 * P.q0;
     P.safe2 = 2500.0 > twoq ? 2500.0 : twoq;

@@ -17,9 +17,10 @@
 //    error); only rounding (1e-16 per step) differs.
 //  * f2 is chosen horizontal, so scene-y = f1y * u: the disk-crossing test (signum y' /=
 //    signum y) is a sign-bit comparison of u, no FP64 work;
-//  * lengths are divided by L = (3.75 h2)^(1/5) per ray, which makes the force constant -0.4:
-//    exactly the factor the |pos|^-5 primitive leaves out (one multiply less per force
-//    evaluation, and the correction polynomial needs one instruction instead of two);
+//  * lengths are divided by L = (3.75 h2 T^2)^(1/5) per ray and time by T = stepSize/2, which
+//    makes the force constant -0.4 -- exactly the factor the |pos|^-5 primitive leaves out (one
+//    multiply less per force evaluation, one instruction less in the correction) -- and the step 2,
+//    so that the step constants are 1, 2, 1/3 and 2/3 (two registers instead of seven);
 //  * |pos|^-5 comes from one MUFU.RSQ64H seed and a first-order correction in 5 DP
 //    instructions instead of sqrt, three multiplies and a divide (force error <= 1.4e-11);
 //  * the stage velocities are eliminated algebraically (p3 = p2 - (h/2)^2 a1, ...) and only a1
@@ -70,37 +71,27 @@ BSB_HD double rsqrt_seed(double x)
 #endif
 }
 
-// Write the seed for x^-1/2 into the HIGH word of y, leaving its low word alone.  MUFU.RSQ64H
-// produces only a high word; letting `y` be one long-lived register pair whose low word was zeroed
-// once saves the "clear the low register" move ptxas otherwise emits for every seed.
-BSB_HD void rsqrt_seed_into(double &y, double x)
-{
-#if defined(__CUDA_ARCH__)
-    asm("{\n\t"
-        ".reg .f64 r;\n\t"
-        ".reg .b32 lo, hi, j1, j2;\n\t"
-        "rsqrt.approx.ftz.f64 r, %1;\n\t"
-        "mov.b64 {j1, hi}, r;\n\t"
-        "mov.b64 {lo, j2}, %0;\n\t"
-        "mov.b64 %0, {lo, hi};\n\t"
-        "}" : "+d"(y) : "d"(x));
-#else
-    y = rsqrt_seed(x);
-#endif
-}
-
 // 0.4 q^(-5/2) (the factor 0.4 is absorbed by the ray's length scale, see ray_frame).  With
 // y0 = q^-1/2 (1+d) from the seed and e = 1 - q y0^2:
 //   q^(-5/2) = y0^5 (1-e)^(-5/2) = y0^5 (1 + 5/2 e + 35/8 e^2 + ...) ~= 2.5 y0^5 (1.4 - q y0^2).
 // The dropped term is 4.375 e^2: |e| <= 2^-19.1 measured on the device (bsb_selftest_rinv5), so
-// the force is low by at most 1.4e-11 relative -- as if h2 were 1.4e-11 smaller, i.e. a deflection
-// error of ~1e-11 rad against the ~1e-7 rad that the 1e-4 parity bar on the star Gaussians
-// allows.  5 FP64 instructions + 1 MUFU.  `k14` must hold 1.4 in a register / the
-// constant bank: an FP64 immediate carries only the high word.
-BSB_HD double rinv5(double q, double &yh, double k14)
+// the force is low by at most 1.4e-11 relative -- as if h2 were that much smaller, i.e. a deflection
+// error of ~1e-11 rad against the ~1e-7 rad that the 1e-4 parity bar on the star Gaussians allows
+// (SURVEY.md S5).  5 FP64 instructions + 1 MUFU.
+// `k14` must hold 1.4 in a register / the constant bank: an FP64 immediate carries only a high word.
+// |p|^2 and the seed for its inverse square root in one go.  (Tried and rejected: letting the seed keep
+// whatever low word its register pair held, which saves the "clear the low word" move ptxas emits for
+// every MUFU.RSQ64H -- 3 instructions per RK4 step fewer, and 3.7 % SLOWER on the B200: the kernel is bound
+// by the FP64 pipe and its register-operand traffic, not by issue slots; profiles/r02_trace_variants.txt.)
+BSB_HD void norm2_seed(double pu, double pv, double &q, double &y0)
 {
-    rsqrt_seed_into(yh, q);
-    const double y0 = yh;
+    q = fma_(pu, pu, pv * pv);
+    y0 = rsqrt_seed(q);
+}
+
+// 0.4 q^(-5/2) from q and a seed y0 ~ q^-1/2 (see rinv5)
+BSB_HD double rinv5_seeded(double q, double y0, double k14)
+{
     const double s = y0 * y0;
     const double c = fma_(-q, s, k14);
     const double s2 = s * s;
@@ -191,12 +182,12 @@ BSB_HD double inv_fifth_root(double a)
 
 // State of one ray between step blocks.  Coordinates are in the ray's own orbital plane,
 // basis (f1, f2) with f2 HORIZONTAL (so scene-y = f1y * u and a disk-plane crossing is a sign
-// change of u), and divided by L = (3.75 h2)^(1/5) so that the equation of motion is
-// p'' = -0.4 p / |p|^5 for every ray (classical RK4 commutes with this linear change of
+// change of u), divided by L = (3.75 h2 T^2)^(1/5) with time in units of T = stepSize / 2, so that
+// the equation of motion is p'' = -0.4 p / |p|^5 and the step is 2 for every ray (classical RK4 commutes with this linear change of
 // variables, so it is still the reference's discrete map).
 struct RayState {
     double u, v;       // position / L in the (f1, f2) basis
-    double du, dv;     // velocity / L
+    double du, dv;     // velocity / L, per HALF STEP (time unit = stepSize / 2)
     double q;          // u^2 + v^2
     double qh, qs;     // horizon and escape thresholds on q: 1/L^2, safe2/L^2
     double acc[4];     // colour accumulated front-to-back (premultiplied RGBA), Raytracer.hs:86
@@ -211,7 +202,7 @@ enum : int32_t { kAlive = 0, kBlack = 1, kSky = 2, kCapped = 3, kIdle = 4 };
 
 struct RayFrame {
     double f1[3], f2[3];
-    double L;          // length scale (3.75 h2)^(1/5)
+    double L;          // length scale (3.75 h2 (stepSize/2)^2)^(1/5)
     double iL;         // 1 / L
     double qh;         // 1 / L^2
     int32_t ysign;
@@ -225,9 +216,10 @@ BSB_HD void ray_frame(const FrameParams &P, const double dir[3], RayFrame &F)
     const double n1 = sub_rn(mul_rn(P.cam[2], dir[0]), mul_rn(P.cam[0], dir[2]));
     const double n2 = sub_rn(mul_rn(P.cam[0], dir[1]), mul_rn(P.cam[1], dir[0]));
     const double h2 = add_rn(add_rn(mul_rn(n0, n0), mul_rn(n1, n1)), mul_rn(n2, n2));  // :73
-    // p'' = -1.5 h2 p/|p|^5 with p = L p~ gives p~'' = -(1.5 h2 / L^5) p~/|p~|^5.  rinv5 returns
-    // 0.4 |p~|^-5, so the force constant wanted is 0.4: L^5 = 1.5 h2 / 0.4 = 3.75 h2
-    double l5 = 3.75 * h2;
+    // p'' = -1.5 h2 p/|p|^5.  With lengths in units of L and time in units of T = stepSize/2 this is
+    // p~'' = -(1.5 h2 T^2 / L^5) p~/|p~|^5.  The kernel's |p|^-5 primitive returns 0.4 |p~|^-5, so the
+    // constant wanted is 0.4: L^5 = 3.75 h2 T^2
+    double l5 = (3.75 * h2) * P.hh2;
     if (!(l5 > 1e-30)) l5 = 1e-30;    // (near-)radial ray: the force is ~1e-30 of anything else either way
     const double iL = inv_fifth_root(l5);
     const double iL2 = iL * iL;
@@ -285,8 +277,9 @@ BSB_HD void ray_init(const FrameParams &P, int x, int y, RayState &s, RayFrame &
     const double iL = F.iL;
     s.u = (P.cam[0] * F.f1[0] + P.cam[1] * F.f1[1] + P.cam[2] * F.f1[2]) * iL;
     s.v = (P.cam[0] * F.f2[0] + P.cam[1] * F.f2[1] + P.cam[2] * F.f2[2]) * iL;
-    s.du = (dir[0] * F.f1[0] + dir[1] * F.f1[1] + dir[2] * F.f1[2]) * iL;
-    s.dv = (dir[0] * F.f2[0] + dir[1] * F.f2[1] + dir[2] * F.f2[2]) * iL;
+    const double iLT = iL * P.hh;     // velocities: length / L per half step
+    s.du = (dir[0] * F.f1[0] + dir[1] * F.f1[1] + dir[2] * F.f1[2]) * iLT;
+    s.dv = (dir[0] * F.f2[0] + dir[1] * F.f2[1] + dir[2] * F.f2[2]) * iLT;
     s.q = P.q0 * F.qh;               // the reference tests quadrance(cam) on the first step
     s.qh = F.qh;
     s.qs = P.safe2 * F.qh;
@@ -357,25 +350,39 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
 // with a_i = g_i p_i (MINUS the acceleration).  Only a1 is formed explicitly; a2, a3, a4 enter as
 // fused multiply-adds:  S = a1 + g2 p2 + g3 p3,  D = g4 p4 - a1,  vel' = vel - h/6 D - h/3 S.
 // The stage velocities are eliminated (p3 = p2 - (h/2)^2 a1, p4 = pe - h (h/2) g2 p2).
+// TIME is measured in half steps (ray_frame), so h = 2, h/2 = (h/2)^2 = 1, h(h/2) = 2, h^2/6 = h/3 =
+// 2/3, h/6 = 1/3: of the step constants only 1/3 and 2/3 need registers (an FP64 instruction can carry
+// 1 and 2 as immediates), which is what keeps every loop constant resident at 2 CTAs per SM.
 BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double &du, double &dv,
-                     double &nu, double &nv, double &nq, double &yh, double k14)
+                     double &nu, double &nv, double &nq, double k14)
 {
-    const double g1 = rinv5(q, yh, k14);
+#if defined(BSB_K3_LITERAL)
+    const double k13 = 1.0 / 3.0, k23 = 2.0 / 3.0;
+#else
+    const double k13 = P.k13, k23 = P.k23;
+#endif
+    const double g1 = rinv5_seeded(q, rsqrt_seed(q), k14);
     const double a1u = g1 * u, a1v = g1 * v;
-    const double p2u = fma_(P.hh, du, u), p2v = fma_(P.hh, dv, v);
-    const double g2 = rinv5(fma_(p2u, p2u, p2v * p2v), yh, k14);
-    const double p3u = fma_(-P.hh2, a1u, p2u), p3v = fma_(-P.hh2, a1v, p2v);
-    const double g3 = rinv5(fma_(p3u, p3u, p3v * p3v), yh, k14);
-    const double peu = fma_(P.h, du, u), pev = fma_(P.h, dv, v);
-    const double c2 = P.hhh * g2;
+    const double p2u = u + du, p2v = v + dv;
+    double q2, y2;
+    norm2_seed(p2u, p2v, q2, y2);
+    const double g2 = rinv5_seeded(q2, y2, k14);
+    const double p3u = p2u - a1u, p3v = p2v - a1v;
+    double q3, y3;
+    norm2_seed(p3u, p3v, q3, y3);
+    const double g3 = rinv5_seeded(q3, y3, k14);
+    const double peu = fma_(2.0, du, u), pev = fma_(2.0, dv, v);
+    const double c2 = g2 + g2;
     const double p4u = fma_(-c2, p2u, peu), p4v = fma_(-c2, p2v, pev);
-    const double g4 = rinv5(fma_(p4u, p4u, p4v * p4v), yh, k14);
+    double q4, y4;
+    norm2_seed(p4u, p4v, q4, y4);
+    const double g4 = rinv5_seeded(q4, y4, k14);
     const double su = fma_(g3, p3u, fma_(g2, p2u, a1u)), sv = fma_(g3, p3v, fma_(g2, p2v, a1v));
     const double du4 = fma_(g4, p4u, -a1u), dv4 = fma_(g4, p4v, -a1v);
-    nu = fma_(-P.hsq6, su, peu);
-    nv = fma_(-P.hsq6, sv, pev);
-    du = fma_(-P.h3, su, fma_(-P.h6, du4, du));
-    dv = fma_(-P.h3, sv, fma_(-P.h6, dv4, dv));
+    nu = fma_(-k23, su, peu);
+    nv = fma_(-k23, sv, pev);
+    du = fma_(-k23, su, fma_(-k13, du4, du));
+    dv = fma_(-k23, sv, fma_(-k13, dv4, dv));
     nq = fma_(nu, nu, nv * nv);
 }
 
@@ -391,8 +398,11 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
     double ua = s.u, va = s.v, qa = s.q, du = s.du, dv = s.dv;
     double ub = ua, vb = va, qb = qa;
-    double yh = 0.0;                                            // seed holder: low word stays 0
+#if defined(BSB_K14_PARAM)
     const double k14 = P.k14;
+#else
+    const double k14 = 1.4;      // as a literal: 0.9 % faster than from the constant bank (profiles/r02_trace_variants.txt)
+#endif
     // q > 0, so doubles order like their bit patterns.  Fast test on the high words: strictly
     // between the two thresholds' high words => neither the horizon nor the escape test fires.
     const long long qh = dbits(s.qh), qs = dbits(s.qs);
@@ -417,18 +427,18 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
         if (remaining == 0) break;
         bool newest_is_b;
         if (first_is_zero) {
-            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k14);       // rare: the camera sits in the disk plane
+            rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, k14);       // rare: the camera sits in the disk plane
             remaining--;
             newest_is_b = true;
         } else {
             for (;;) {
-                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, yh, k14);
+                rk4_step(P, ua, va, qa, du, dv, ub, vb, qb, k14);
                 remaining--;
                 if (((((hi32(ub) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qb) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = true;
                     break;
                 }
-                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, yh, k14);
+                rk4_step(P, ub, vb, qb, du, dv, ua, va, qa, k14);
                 remaining--;
                 if (((((hi32(ua) ^ side_word) & dmask) < 0) | ((unsigned)(hi32(qa) - lo_hi) >= span) | (remaining == 0)) != 0) {
                     newest_is_b = false;

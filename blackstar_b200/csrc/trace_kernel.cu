@@ -282,10 +282,9 @@ __global__ void rinv5_selftest_kernel(double q_lo, double q_hi, int n, double *m
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double q = q_lo * exp(lr * ((double)i + 0.5) / (double)n);
         const double ref = 0.4 * pow(q, -2.5);
-        double yh = 0.0;
-        const double got = rinv5(q, yh, 1.4);
-        worst = fmax(worst, fabs(got - ref) / ref);
         const double y0 = rsqrt_seed(q);
+        const double got = rinv5_seeded(q, y0, 1.4);
+        worst = fmax(worst, fabs(got - ref) / ref);
         worst_seed = fmax(worst_seed, fabs(fma(-q * y0, y0, 1.0)));
     }
 #pragma unroll

@@ -107,6 +107,6 @@ int hc_trace_ray(void *p, const bsb_camera *cam, const bsb_scene *scn, int gx, i
     return 0;
 }
 
-double hc_rinv5(double q) { double yh = 0.0; return rinv5(q, yh, 1.4); }
+double hc_rinv5(double q) { return rinv5_seeded(q, rsqrt_seed(q), 1.4); }
 
 }  // extern "C"

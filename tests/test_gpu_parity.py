@@ -413,6 +413,25 @@ def test_full_size_rows_default_aa_4096(rnd, scenes_dir):
     assert np.isfinite(full).all()
 
 
+def test_whole_headline_frame_vs_oracle(rnd, scenes_dir):
+    """EVERY pixel of the 4096x4096 default-aa frame (67 M rays, stars, disk, photon ring) against the
+    oracle, which takes about a minute on the box's host cores.  The contract is 1e-4 per channel; the
+    count of pixels above tighter bars is printed so that a drift shows up long before it matters."""
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default-aa.yaml"), 4096, 4096)
+    stars = starmap.synthetic_stars()
+    rnd.set_stars(stars)
+    rnd.set_option("trace_variant", 6)
+    got = rnd.render(cfg)
+    st = rnd.last_stats
+    ref, rsteps = po.render(cfg, po.Tree(stars))
+    err = np.abs(rgb(got) - ref).max(axis=2)
+    print(f"whole frame: max err {err.max():.3e}; pixels > 1e-4: {(err > 1e-4).sum()}, > 1e-5: {(err > 1e-5).sum()}, "
+          f"> 1e-6: {(err > 1e-6).sum()} of {err.size}")
+    assert err.max() < TOL
+    assert (err > 1e-5).sum() <= 16
+    assert st["steps"] == rsteps - 4 * 4096 * 4096     # identical step counts (minus the unused last step of every ray)
+
+
 def test_full_size_rows_lensing_disk_8192(rnd, scenes_dir):
     # BASELINE config 4: lensing-disk.yaml at 8192x8192 (x4 supersampling): bands of rows vs the oracle,
     # and the bloom of an 8192-wide frame (the 16-pixels-per-thread variant of the bloom kernel)
