@@ -329,6 +329,20 @@ def test_pageable_and_pinned_host_buffers_give_the_same_frame(rnd, scenes_dir, s
     np.testing.assert_array_equal(rnd.do_render_srgb8(cfg, out=p8.numpy()), rnd.do_render_srgb8(cfg))
 
 
+@pytest.mark.parametrize("scene", SCENES)
+def test_ghc_crosscheck_expectations(rnd, scenes_dir, scene):
+    """The CUDA path renders the committed cross-check images (tools/ghc_crosscheck/expected: what the real
+    reference is to be diffed against by someone with GHC): `--preview` of every scene, RGB8."""
+    from PIL import Image
+    exp = np.asarray(Image.open(os.path.join(HERE, "..", "tools", "ghc_crosscheck", "expected", f"prev-{scene}.png")).convert("RGB"))
+    cfg = config.prepare_scene(config.load_config(f"{scenes_dir}/{scene}.yaml"), True)
+    rnd.set_stars(starmap.synthetic_stars())
+    got = rnd.do_render_srgb8(cfg)
+    assert got.shape == exp.shape
+    d = np.abs(got.astype(int) - exp.astype(int))
+    assert d.max() <= 1 and (d.max(axis=2) > 0).mean() < 2e-3   # float32 framebuffer vs the oracle's f64: rare 1-LSB flips
+
+
 def test_invalid_arguments_return_status_not_crash(rnd, scenes_dir):
     cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 32, 18)
     with pytest.raises(_lib.BlackstarError):
