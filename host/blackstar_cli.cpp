@@ -25,6 +25,7 @@
 #include <mutex>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -215,7 +216,12 @@ private:
     struct Job { std::string path; std::vector<uint8_t> rgb; int w, h; };
     static void write(const std::string &path, const std::vector<uint8_t> &rgb, int w, int h)
     {
-        const std::string err = pngw::write_rgb8_parallel(path, rgb.data(), w, h);
+        // zlib level and deflate threads of the PNG encoder: the defaults reproduce what the reference's encoder
+        // spends (level 6); a batch that is bound by the encoder (600-frame animations: profiles/) can trade
+        // file size for speed with BSB_PNG_LEVEL=1
+        static const int level = [] { const char *e = std::getenv("BSB_PNG_LEVEL"); const int v = e ? std::atoi(e) : 6; return v < 0 || v > 9 ? 6 : v; }();
+        static const int threads = [] { const char *e = std::getenv("BSB_PNG_THREADS"); return e ? std::max(0, std::atoi(e)) : 0; }();
+        const std::string err = pngw::write_rgb8_parallel(path, rgb.data(), w, h, threads, level);
         if (!err.empty()) std::cout << err << std::endl;
     }
     void run()

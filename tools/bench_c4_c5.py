@@ -74,11 +74,11 @@ def run_c4(n, steps, warmup):
     return out
 
 
-def run_c5(n, n_frames, keep_png):
+def run_c5(n, n_frames, keep_png, png_level=6):
     from blackstar_b200 import animation, config, starmap
     from blackstar_b200.render import Renderer
     work = tempfile.mkdtemp(prefix="bsb_c5_")
-    rep = {"frames": n_frames, "gpus": n, "resolution": [1920, 1080]}
+    rep = {"frames": n_frames, "gpus": n, "resolution": [1920, 1080], "png_zlib_level": png_level}
     try:
         anim = animation.load_animation(os.path.join(ROOT, "animations", "default-ani.yaml"))
         anim.nFrames = n_frames
@@ -99,7 +99,8 @@ def run_c5(n, n_frames, keep_png):
         procs = []
         t0 = time.perf_counter()
         for k in range(n):
-            env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(k))
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(k), BSB_PNG_LEVEL=str(png_level),
+                       BSB_PNG_THREADS=str(max(1, (os.cpu_count() or 8) // n)))
             procs.append(subprocess.Popen([exe, "-f", "-s", ppm, "-o", os.path.join(work, f"out{k}"), os.path.join(work, f"in{k}")],
                                           env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
         errs = [p.communicate()[1] for p in procs]
@@ -165,7 +166,8 @@ def main():
     if not a.skip_c4:
         rep["C4_lensing_disk_8192"] = run_c4(n, a.steps, a.warmup)
     if not a.skip_c5:
-        rep["C5_animation"] = run_c5(n, a.frames, a.keep_png)
+        rep["C5_animation"] = run_c5(n, a.frames, a.keep_png, 6)
+        rep["C5_animation_png_level1"] = run_c5(n, a.frames, "", 1)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(rep, open(a.out, "w"), indent=1)
     brief = {"gpus": n}
@@ -177,6 +179,7 @@ def main():
         brief["C4 stats"] = c4.get("bsb_stats_srgb8")
     if "C5_animation" in rep:
         brief["C5"] = {k: rep["C5_animation"].get(k) for k in ("with_png", "render_only", "bottleneck")}
+        brief["C5 zlib level 1"] = rep["C5_animation_png_level1"].get("with_png")
     print(json.dumps(brief, indent=1))
 
 
