@@ -1140,14 +1140,19 @@ extern "C" int bsb_render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const
     return render_full_device(ctx, cam, scn, &st, want_float != 0, want_rgb8 != 0, res);
 }
 
-// Blocks until everything queued on the ctx's GPUs has finished.
+// Blocks until everything queued on the ctx's GPUs has finished.  Returns BSB_ERR_STEPCAP if a ray of the
+// LAST trace launch on any of them was stopped by the step cap -- the one thing the asynchronous entry
+// points (bsb_render_device without stats, bsb_render_full_device) cannot report when they return.
 extern "C" int bsb_synchronize(bsb_ctx *ctx)
 {
     if (!ctx) return BSB_ERR_INVALID;
+    unsigned long long capped = 0;
     for (DeviceState &d : ctx->devs) {
         BSB_CUDA(ctx, cudaSetDevice(d.dev));
         BSB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        capped += d.h_ctr->capped;
     }
+    if (capped) return fail(ctx, BSB_ERR_STEPCAP, "a ray reached the step cap (the reference would not terminate)");
     return BSB_OK;
 }
 

@@ -310,7 +310,7 @@ class DistributedFrame:
             src = self.tile8 if rgb8 else self.tile
             if r1 > r0:
                 self.r.download_2d(host.ptr + r0 * self.W * px, self.W * px, src.data_ptr(), self.W * px, self.W * px, r1 - r0)
-        torch.cuda.current_stream(self.device).synchronize()
+        self.r.synchronize()          # also surfaces BSB_ERR_STEPCAP of this frame's (asynchronous) trace launch
         if self.world > 1:
             dist.barrier()
         return host.array

@@ -157,6 +157,8 @@ int bsb_render_full(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
 /* Same work, frame left on the GPU(s); asynchronous (bsb_synchronize waits for it). */
 int bsb_render_full_device(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
                            int want_float, int want_rgb8);
+/* Waits for everything queued on the ctx's GPUs; BSB_ERR_STEPCAP if the last trace launch capped a ray
+ * (the asynchronous entry points cannot report that when they return). */
 int bsb_synchronize(bsb_ctx *ctx);
 
 /* ---- writeImg's pixel map (src/Raytracer.hs:23-32): sRGB then toWord8, RGB8 out ------- */

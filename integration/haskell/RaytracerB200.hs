@@ -9,7 +9,7 @@
 --     other-modules:   RaytracerB200
 --     extra-libraries: blackstar_b200
 --     build-depends:   ... , storable-record or hand-written Storable instances as below
-module RaytracerB200 (withB200, renderB200, bloomB200, B200) where
+module RaytracerB200 (withB200, renderB200, renderB200Word8, bloomB200, B200) where
 
 import Foreign
 import Foreign.C.Types
@@ -32,6 +32,8 @@ foreign import ccall safe "bsb_last_error"  c_lastError :: Ptr Ctx -> IO CString
 foreign import ccall safe "bsb_set_stars"   c_setStars  :: Ptr Ctx -> Ptr CStar -> CSize -> IO CInt
 foreign import ccall safe "bsb_render_full" c_renderFull
     :: Ptr Ctx -> Ptr CCamera -> Ptr CScene -> Ptr CFloat -> Ptr () -> IO CInt
+foreign import ccall safe "bsb_render_full_srgb8" c_renderFullSrgb8
+  :: Ptr Ctx -> Ptr CCamera -> Ptr CScene -> Ptr Word8 -> Ptr () -> IO CInt
 foreign import ccall safe "bsb_render"      c_render
     :: Ptr Ctx -> Ptr CCamera -> Ptr CScene -> CInt -> CInt -> Ptr CFloat -> Ptr () -> IO CInt
 foreign import ccall safe "bsb_bloom"       c_bloom
@@ -103,6 +105,23 @@ renderB200 (B200 ctx) cfg = do
   with (CCamera (camera cfg)) $ \cp -> with (CScene (scene cfg)) $ \sp ->
     withForeignPtr buf $ \bp -> check ctx =<< c_renderFull ctx cp sp bp nullPtr
   return $ floatsToImage w h (VS.unsafeFromForeignPtr0 buf (4 * w * h))
+
+-- | Everything Main.doRender does INCLUDING writeImg's pixel map (app/Main.hs:105-123,
+--   src/Raytracer.hs:23-32): render, supersample, bloom, sRGB, toWord8 -- the RGB8 image the PNG encoder
+--   takes.  The sRGB + toWord8 map runs in the epilogue of the last bloom launch, the float frame is never
+--   written and only 3 bytes per pixel cross PCIe; `doRender` then becomes
+--       img8 <- timeAction "Rendering" =<< renderB200Word8 b200 cfg
+--       writeArray PNG def outName img8        -- instead of writeImg (no `A.map (toWord8 . fmap sRGB)`)
+--   This is the call bench.py times as `e2e` (with the same plain-malloc buffer mallocForeignPtrArray gives).
+renderB200Word8 :: B200 -> Config -> IO (Image S RGB Word8)
+renderB200Word8 (B200 ctx) cfg = do
+  let (w, h) = resolution (scene cfg)
+  buf <- mallocForeignPtrArray (3 * w * h) :: IO (ForeignPtr Word8)
+  with (CCamera (camera cfg)) $ \cp -> with (CScene (scene cfg)) $ \sp ->
+    withForeignPtr buf $ \bp -> check ctx =<< c_renderFullSrgb8 ctx cp sp bp nullPtr
+  let v = VS.unsafeFromForeignPtr0 buf (3 * w * h)
+  return $ makeArrayR S Seq (h :. w) $ \(y :. x) ->
+    let o = 3 * (y * w + x) in PixelRGB (v VS.! o) (v VS.! (o + 1)) (v VS.! (o + 2))
 
 -- | ImageFilters.bloom strength divider img
 bloomB200 :: B200 -> Double -> Int -> Image U RGB Double -> IO (Image U RGB Double)

@@ -5,7 +5,11 @@
 #include "../../blackstar_b200/csrc/host_setup.hpp"
 #include "../../blackstar_b200/csrc/trace_core.cuh"
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 using namespace bsb;
@@ -105,6 +109,39 @@ int hc_trace_ray(void *p, const bsb_camera *cam, const bsb_scene *scn, int gx, i
     *steps = s.steps;
     *status = s.status;
     return 0;
+}
+
+// StarMap.readMap + starColor' as the library parses a PPM catalogue: n stars, or -1 with the message in err
+long hc_parse_ppm(const uint8_t *bytes, size_t len, bsb_star *out, size_t cap, char *err, size_t errcap)
+{
+    std::vector<bsb_star> v;
+    std::string e;
+    if (!parse_ppm(bytes, len, v, e)) {
+        std::snprintf(err, errcap, "%s", e.c_str());
+        return -1;
+    }
+    for (size_t k = 0; k < v.size() && k < cap; k++) out[k] = v[k];
+    return (long)v.size();
+}
+
+// wall-clock milliseconds of build_star_tree (what bsb_set_stars spends on the host before the upload)
+double hc_build_tree_ms(const bsb_star *stars, size_t n, int reps)
+{
+    double best = 1e30;
+    for (int r = 0; r < reps; r++) {
+        HostStarTree t;
+        const auto t0 = std::chrono::steady_clock::now();
+        build_star_tree(stars, n, t);
+        best = std::min(best, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+    return best;
+}
+
+const char *hc_validate_stars(const bsb_star *stars, size_t n)
+{
+    static thread_local std::string msg;
+    msg = validate_stars(stars, n);
+    return msg.c_str();
 }
 
 double hc_rinv5(double q) { return rinv5_seeded(q, rsqrt_seed(q), 1.4); }

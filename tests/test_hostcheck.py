@@ -200,3 +200,45 @@ def test_random_scenes_match_oracle(hc, seed):
     assert steps == rsteps - nrays, cfg
     np.testing.assert_array_equal(got, got_b)
     assert steps_b == steps
+
+
+def test_ppm_parser_equals_the_oracles_and_rejects_other_files(hc):
+    """parse_ppm (what bsb_set_stars_ppm runs) against the oracle's restatement of StarMap.readMap
+    (src/StarMap.hs:45-75) on the same bytes; and the refusals: a ragged length, random bytes, NaNs."""
+    hc.hc_parse_ppm.restype = ctypes.c_long
+    hc.hc_parse_ppm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    data = starmap.synthetic_catalogue(50000, seed=21)
+    want = po.read_ppm(data)
+    out = np.zeros(50000, dtype=starmap.STAR_DTYPE)
+    err = ctypes.create_string_buffer(256)
+    n = hc.hc_parse_ppm(data, len(data), out.ctypes.data, len(out), err, 256)
+    assert n == 50000
+    for f in ("pos", "mag", "hue", "sat"):
+        np.testing.assert_array_equal(out[f], want[f])
+    np.testing.assert_array_equal(out["pos"], starmap.read_ppm(data)["pos"])
+    # refusals (ADVICE r1: a stars.kdt or any other file used to render a garbage sky with rc = 0)
+    assert hc.hc_parse_ppm(data[:-3], len(data) - 3, out.ctypes.data, len(out), err, 256) == -1 and b"PPM-format" in err.value
+    rng = np.random.default_rng(5)
+    junk = rng.integers(0, 256, 28 + 28 * 2000, dtype=np.uint8).tobytes()
+    assert hc.hc_parse_ppm(junk, len(junk), out.ctypes.data, len(out), err, 256) == -1 and b"not a star" in err.value
+    assert hc.hc_parse_ppm(b"tiny", 4, out.ctypes.data, len(out), err, 256) == -1
+    # the flat-list entry point validates too
+    hc.hc_validate_stars.restype = ctypes.c_char_p
+    hc.hc_validate_stars.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    assert hc.hc_validate_stars(out.ctypes.data, len(out)) == b""
+    bad = out.copy()
+    bad["pos"][7] = [np.nan, 0, 0]
+    assert b"star 7" in hc.hc_validate_stars(bad.ctypes.data, len(bad))
+    bad = out.copy()
+    bad["hue"][9] = 1.25
+    assert b"star 9" in hc.hc_validate_stars(bad.ctypes.data, len(bad))
+
+
+def test_star_tree_build_time(hc):
+    """N3: the host-side tree build that replaces `generate-tree` (src/StarMap.hs:90-91) on the full catalogue."""
+    hc.hc_build_tree_ms.restype = ctypes.c_double
+    hc.hc_build_tree_ms.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    stars = starmap.synthetic_stars()
+    ms = hc.hc_build_tree_ms(stars.ctypes.data, len(stars), 3)
+    print(f"build_star_tree({len(stars)} stars): {ms:.1f} ms on this host")
+    assert ms < 1500
