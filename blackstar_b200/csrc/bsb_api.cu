@@ -340,7 +340,9 @@ int copy_bands_to_host(bsb_ctx *ctx, void *dst, size_t row_bytes, int rows, cons
     const cudaError_t pe = cudaPointerGetAttributes(&attr, dst);
     if (pe != cudaSuccess) (void)cudaGetLastError();
     const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
-    if (pinned || bytes < kStageChunk / 4 || ctx->copy_threads <= 0) {
+    // small frames (a 1080p RGB8 image is 6 MB) are not worth waking the copy threads for: the driver's own
+    // staged copy takes well under a millisecond, and batch jobs run one such process per GPU
+    if (pinned || bytes < 2 * kStageChunk || ctx->copy_threads <= 0) {
         for (const Band &b : bands) {
             BSB_CUDA(ctx, cudaSetDevice(b.d->dev));
             uint8_t *row = out + (size_t)b.row0 * row_bytes;

@@ -343,6 +343,35 @@ def test_ghc_crosscheck_expectations(rnd, scenes_dir, scene):
     assert d.max() <= 1 and (d.max(axis=2) > 0).mean() < 2e-3   # float32 framebuffer vs the oracle's f64: rare 1-LSB flips
 
 
+def test_step_cap_is_an_option_and_is_reported_on_every_path(rnd, scenes_dir):
+    """The reference has no iteration cap (src/Raytracer.hs:80-85); ours is a safety net the caller can move
+    ("step_cap").  A capped ray must surface as BSB_ERR_STEPCAP on the synchronous calls AND, through
+    bsb_synchronize, on the asynchronous ones (the async path used to drop it)."""
+    import torch
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 64, 36)
+    rnd.set_stars(None)
+    ok = rnd.render(cfg)
+    rnd.set_option("step_cap", 100)            # every ray of this scene needs > 200 steps
+    try:
+        with pytest.raises(_lib.BlackstarError) as e:
+            rnd.render(cfg)
+        assert e.value.code == 5 and rnd.last_stats["capped"] > 1000   # the rays that fall in within 100 steps are not capped
+        with pytest.raises(_lib.BlackstarError) as e:
+            rnd.do_render(cfg)
+        assert e.value.code == 5
+        buf = torch.empty((36, 64, 4), device="cuda")
+        rnd.render_device(cfg, buf.data_ptr())               # asynchronous: returns before the kernel has run
+        with pytest.raises(_lib.BlackstarError) as e:
+            rnd.synchronize()
+        assert e.value.code == 5
+    finally:
+        rnd.set_option("step_cap", 1000000)
+    np.testing.assert_array_equal(rnd.render(cfg), ok)
+    rnd.synchronize()
+    with pytest.raises(_lib.BlackstarError):
+        rnd.set_option("step_cap", 0)
+
+
 def test_invalid_arguments_return_status_not_crash(rnd, scenes_dir):
     cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 32, 18)
     with pytest.raises(_lib.BlackstarError):
