@@ -75,7 +75,7 @@ def main(argv=None) -> int:
             r.set_stars(starmap.synthetic_stars())
         else:
             with open(args.starmap, "rb") as f:
-                r.set_stars_ppm(f.read())
+                r.set_stars_file(f.read())   # stars.kdt (the reference's tree file) or the PPM catalogue
     except Exception as e:  # app/Main.hs:50
         print(f"Error decoding star tree: \n{e}")
         return 1

@@ -19,7 +19,7 @@ SYMBOLS = [
     "bsb_render_device", "bsb_bloom", "bsb_bloom_device", "bsb_render_full", "bsb_to_srgb8",
     "bsb_to_srgb8_device", "bsb_render_full_srgb8", "bsb_measure_fp64_peak", "bsb_measure_hbm_copy",
     "bsb_selftest_rinv5", "bsb_render_full_both", "bsb_render_full_device", "bsb_synchronize",
-    "bsb_bloom_h_device", "bsb_bloom_v_device", "bsb_bloom_to_device", "bsb_download_2d",
+    "bsb_bloom_h_device", "bsb_bloom_v_device", "bsb_bloom_to_device", "bsb_download_2d", "bsb_set_stars_file",
 ]
 
 
@@ -67,6 +67,7 @@ def load() -> ctypes.CDLL:
     L.bsb_set_option.argtypes = [vp, cp, d]; L.bsb_set_option.restype = i
     L.bsb_set_stars.argtypes = [vp, vp, sz]; L.bsb_set_stars.restype = i
     L.bsb_set_stars_ppm.argtypes = [vp, cp, sz]; L.bsb_set_stars_ppm.restype = i
+    L.bsb_set_stars_file.argtypes = [vp, cp, sz]; L.bsb_set_stars_file.restype = i
     L.bsb_star_count.argtypes = [vp]; L.bsb_star_count.restype = sz
     L.bsb_render.argtypes = [vp, vp, vp, i, i, vp, vp]; L.bsb_render.restype = i
     L.bsb_render_device.argtypes = [vp, vp, vp, i, i, vp, vp]; L.bsb_render_device.restype = i

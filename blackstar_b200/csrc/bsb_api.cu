@@ -667,6 +667,16 @@ extern "C" int bsb_set_stars_ppm(bsb_ctx *ctx, const uint8_t *bytes, size_t len)
     return bsb_set_stars(ctx, stars.data(), stars.size());
 }
 
+extern "C" int bsb_set_stars_file(bsb_ctx *ctx, const uint8_t *bytes, size_t len)
+{
+    if (!ctx) return BSB_ERR_INVALID;
+    if (!bytes) return fail(ctx, BSB_ERR_INVALID, "bsb_set_stars_file: NULL buffer");
+    std::vector<bsb_star> stars;
+    std::string err;
+    if (!parse_star_file(bytes, len, stars, err)) return fail(ctx, BSB_ERR_INVALID, "Error decoding star map: " + err);
+    return bsb_set_stars(ctx, stars.data(), stars.size());
+}
+
 extern "C" size_t bsb_star_count(const bsb_ctx *ctx) { return ctx ? ctx->n_stars : 0; }
 
 // ======================================================================== render

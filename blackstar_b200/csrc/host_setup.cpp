@@ -327,6 +327,108 @@ bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std
     return true;
 }
 
+// ------------------------------------------------------------------ stars.kdt (the reference's tree file)
+// What `generate-tree` writes (app/GenerateTree.hs:11-29): Data.Serialize.encode of a
+//     KdMap Double (V3 Double) (Int, Char)                                     (src/StarMap.hs:28-41, 87-88)
+// through cereal's Generic instances.  NEITHER cereal NOR kdt is under /root/reference and there is no GHC in
+// this image, so the byte layout below is RECALLED from the packages' sources (cereal-0.5.8, kdt-0.2.4), not
+// verified -- which is why the reader checks everything the format lets it check and refuses the file
+// otherwise, rather than rendering a wrong sky:
+//   KdMap    = pointAsList fn (Word8 0, :33-35) ++ distSqr fn (Word8 0, :38-40) ++ root TreeNode ++ size (Int = Int64 BE)
+//   TreeNode = Word8 tag: 0 -> left TreeNode ++ point (3 x Float64 BE) ++ (mag Int64 BE, spectral Char as UTF-8)
+//                              ++ axisValue (Float64 BE) ++ right TreeNode
+//                         1 -> Empty
+// Checks: tags are 0/1; every point is a finite unit vector; axisValue is, bit for bit, the point's
+// coordinate on axis (depth mod 3) (kdt cycles the axes and stores the node's own coordinate); left/right
+// points respect the split; the node count equals `size`; the input is consumed exactly.
+namespace {
+
+struct KdtReader {
+    const uint8_t *p, *end;
+    std::vector<bsb_star> *out;
+    std::string err;
+    size_t nodes = 0;
+
+    bool need(size_t n) { if ((size_t)(end - p) < n) { err = "truncated"; return false; } return true; }
+    bool f64(double &d) { if (!need(8)) return false; d = f64be(p); p += 8; return true; }
+    bool i64(int64_t &v) { if (!need(8)) return false; uint64_t u = 0; for (int k = 0; k < 8; k++) u = (u << 8) | p[k]; p += 8; v = (int64_t)u; return true; }
+    bool chr(int &c)
+    {
+        if (!need(1)) return false;
+        const int b = *p++;
+        if (b < 0x80) { c = b; return true; }
+        const int extra = b >= 0xf0 ? 3 : (b >= 0xe0 ? 2 : 1);
+        if (!need((size_t)extra)) return false;
+        c = b & (0x3f >> extra);
+        for (int k = 0; k < extra; k++) c = (c << 6) | (*p++ & 0x3f);
+        return true;
+    }
+    // lo/hi: bounds the ancestors' splits put on each coordinate
+    bool node(int depth, double lo[3], double hi[3])
+    {
+        if (depth > 200) { err = "tree deeper than 200 levels"; return false; }
+        if (!need(1)) return false;
+        const int tag = *p++;
+        if (tag == 1) return true;
+        if (tag != 0) { err = "constructor tag is neither TreeNode (0) nor Empty (1)"; return false; }
+        // the left subtree comes first, but its bound is this node's axis value, which comes after it:
+        // remember where the left subtree starts, skip ahead structurally by parsing it with open bounds,
+        // then check it against the split afterwards via the recorded extent
+        const size_t first = out->size();
+        double l_lo[3] = { lo[0], lo[1], lo[2] }, l_hi[3] = { hi[0], hi[1], hi[2] };
+        if (!node(depth + 1, l_lo, l_hi)) return false;
+        const size_t mid = out->size();
+        bsb_star s;
+        int64_t mag;
+        int ch;
+        double axis_value;
+        if (!f64(s.pos[0]) || !f64(s.pos[1]) || !f64(s.pos[2]) || !i64(mag) || !chr(ch) || !f64(axis_value)) return false;
+        const double q = s.pos[0] * s.pos[0] + s.pos[1] * s.pos[1] + s.pos[2] * s.pos[2];
+        if (!std::isfinite(q) || std::fabs(q - 1.0) > 1e-9) { err = "a point is not a unit vector"; return false; }
+        const int ax = depth % 3;
+        if (std::memcmp(&axis_value, &s.pos[ax], 8) != 0) { err = "axisValue is not the point's coordinate on axis (depth mod 3)"; return false; }
+        if (mag < -32768 || mag > 32767) { err = "magnitude outside the catalogue's int16 range"; return false; }
+        for (int a = 0; a < 3; a++)
+            if (s.pos[a] < lo[a] || s.pos[a] > hi[a]) { err = "a point lies on the wrong side of an ancestor's split"; return false; }
+        for (size_t k = first; k < mid; k++)
+            if ((*out)[k].pos[ax] > axis_value) { err = "a left-subtree point lies right of its node's split"; return false; }
+        s.mag = (int32_t)mag;
+        s.pad_ = 0;
+        spectral_colour(ch, s.hue, s.sat);       // starColor' as readTreeFromFile applies it (:85)
+        out->push_back(s);
+        nodes++;
+        double r_lo[3] = { lo[0], lo[1], lo[2] }, r_hi[3] = { hi[0], hi[1], hi[2] };
+        r_lo[ax] = axis_value;
+        return node(depth + 1, r_lo, r_hi);
+    }
+};
+
+}  // namespace
+
+bool parse_kdt(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err)
+{
+    out.clear();
+    KdtReader r{ bytes, bytes + len, &out, "" };
+    if (len < 11 || bytes[0] != 0 || bytes[1] != 0) { err = "not a stars.kdt tree file (it starts with the two placeholder bytes 00 00)"; return false; }
+    r.p += 2;
+    double lo[3] = { -2, -2, -2 }, hi[3] = { 2, 2, 2 };
+    int64_t size = 0;
+    if (!r.node(0, lo, hi) || !r.i64(size)) { err = "stars.kdt: " + (r.err.empty() ? std::string("malformed") : r.err); out.clear(); return false; }
+    if ((uint64_t)size != r.nodes) { err = "stars.kdt: the stored size does not match the number of tree nodes"; out.clear(); return false; }
+    if (r.p != r.end) { err = "stars.kdt: bytes left over after the tree"; out.clear(); return false; }
+    return true;
+}
+
+// A star map file as --starmap names it: the reference's tree file (stars.kdt) or the PPM catalogue it was made from.
+bool parse_star_file(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err)
+{
+    std::string e1, e2;
+    if (parse_kdt(bytes, len, out, e1)) return true;
+    if (parse_ppm(bytes, len, out, e2)) return true;
+    err = "neither a stars.kdt tree file (" + e1 + ") nor a PPM catalogue (" + e2 + ")";
+    return false;
+}
+
 // The star list handed to bsb_set_stars: unit vectors, finite colours, hue in [0, 1) (massiv-io's
 // toPixelRGB raises `error` outside it).  NaNs would also break the strict weak ordering nth_element needs.
 std::string validate_stars(const bsb_star *stars, size_t n)

@@ -32,6 +32,11 @@ void build_star_tree(const bsb_star *stars, size_t n, HostStarTree &out);
 // StarMap.readMap + starColor' : PPM binary catalogue -> flat star list.
 bool parse_ppm(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err);
 
+// The reference's tree file (stars.kdt = cereal encoding of kdt's KdMap; layout recalled, every structural
+// invariant checked) -> flat star list with starColor' applied; parse_star_file tries it, then the PPM layout.
+bool parse_kdt(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err);
+bool parse_star_file(const uint8_t *bytes, size_t len, std::vector<bsb_star> &out, std::string &err);
+
 // "" if every star is a finite unit vector with a colour inside the HSI domain, else what is wrong
 std::string validate_stars(const bsb_star *stars, size_t n);
 

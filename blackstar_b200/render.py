@@ -88,6 +88,10 @@ class Renderer:
     def set_stars_ppm(self, data: bytes):
         self._check(self._L.bsb_set_stars_ppm(self._ctx, data, len(data)))
 
+    def set_stars_file(self, data: bytes):
+        """The file ``--starmap`` names: the reference's stars.kdt tree file or a PPM catalogue."""
+        self._check(self._L.bsb_set_stars_file(self._ctx, data, len(data)))
+
     @property
     def star_count(self) -> int:
         return int(self._L.bsb_star_count(self._ctx))

@@ -114,3 +114,50 @@ def synthetic_catalogue(n: int = DEFAULT_N_STARS, seed: int = DEFAULT_SEED) -> b
 def synthetic_stars(n: int = DEFAULT_N_STARS, seed: int = DEFAULT_SEED) -> np.ndarray:
     """``read_ppm(synthetic_catalogue(n, seed))``"""
     return read_ppm(synthetic_catalogue(n, seed))
+
+
+# ---------------------------------------------------------------------------------------- stars.kdt
+def _put_char(c: int) -> bytes:
+    return chr(c).encode("utf-8")          # cereal's Char encoding is UTF-8
+
+
+def write_kdt(pos: np.ndarray, mag: np.ndarray, spectral: np.ndarray) -> bytes:
+    """What ``generate-tree`` writes (src/StarMap.hs:87-91): ``encode (build toList stars)``.
+
+    The tree is built as kdt-0.2.4 builds it (sort by the axis of the level, axes cycling x, y, z; the element
+    at index n ``div`` 2 becomes the node) and encoded as cereal's Generic instances do -- both RECALLED, not
+    verified (no GHC here; see csrc/host_setup.cpp: parse_kdt).  Used by the tests and by anyone who wants a
+    tree file from a catalogue without running the Haskell tool."""
+    import struct
+    import sys
+    out = bytearray(b"\x00\x00")            # the two function fields (src/StarMap.hs:33-40)
+    pos = np.asarray(pos, dtype=np.float64)
+    sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
+
+    def node(idx: np.ndarray, depth: int):
+        if len(idx) == 0:
+            out.append(1)                    # Empty
+            return
+        ax = depth % 3
+        order = idx[np.argsort(pos[idx, ax], kind="stable")]
+        m = len(order) // 2
+        k = int(order[m])
+        out.append(0)                        # TreeNode
+        node(order[:m], depth + 1)
+        out.extend(struct.pack(">3d", *pos[k]))
+        out.extend(struct.pack(">q", int(mag[k])))
+        out.extend(_put_char(int(spectral[k])))
+        out.extend(struct.pack(">d", float(pos[k, ax])))
+        node(order[m + 1:], depth + 1)
+
+    node(np.arange(len(pos)), 0)
+    out.extend(struct.pack(">q", len(pos)))
+    return bytes(out)
+
+
+def catalogue_to_kdt(ppm: bytes) -> bytes:
+    """``generate-tree PPM stars.kdt`` (app/GenerateTree.hs:11-29) in one call."""
+    n = (len(ppm) - PPM_HEADER_BYTES) // PPM_RECORD_BYTES
+    rec = np.frombuffer(ppm, dtype=_PPM_REC, count=n, offset=PPM_HEADER_BYTES)
+    pos = ra_dec_to_cartesian(rec["ra"].astype("<f8"), rec["dec"].astype("<f8"))
+    return write_kdt(pos, rec["mag"].astype(np.int64), rec["spectral"])

@@ -287,7 +287,7 @@ int usage(int rc)
                  "  -p --preview         preview render (small size)\n"
                  "  -o --output=PATH     output directory\n"
                  "  -f --force           overwrite images without asking\n"
-                 "  -s --starmap=PATH    path to starmap (PPM-format binary catalogue)\n"
+                 "  -s --starmap=PATH    path to starmap (stars.kdt tree file or PPM-format catalogue)\n"
                  "  -? --help            Display help message\n";
     return rc;
 }
@@ -366,7 +366,7 @@ int main(int argc, char **argv)
     }
     bsb_ctx *ctx = bsb_create(0);
     if (!ctx) { std::cout << bsb_last_error(nullptr) << std::endl; return 1; }
-    if (bsb_set_stars_ppm(ctx, reinterpret_cast<const uint8_t *>(catalogue.data()), catalogue.size()) != BSB_OK) {
+    if (bsb_set_stars_file(ctx, reinterpret_cast<const uint8_t *>(catalogue.data()), catalogue.size()) != BSB_OK) {
         std::cout << "Error decoding star tree: \n" << bsb_last_error(ctx) << std::endl;
         bsb_destroy(ctx);
         return 1;

@@ -126,6 +126,11 @@ int bsb_set_stars(bsb_ctx *ctx, const bsb_star *stars, size_t n);
 /* Same, straight from a PPM-format binary catalogue (28-byte header + 28-byte records) as
  * StarMap.readMap parses it (src/StarMap.hs:45-58), applying starColor' (:60-72). */
 int bsb_set_stars_ppm(bsb_ctx *ctx, const uint8_t *bytes, size_t len);
+/* The file `--starmap` names (app/Main.hs:36,46-50), whichever it is: the reference's tree file stars.kdt
+ * (what generate-tree writes: cereal's encoding of kdt's KdMap, src/StarMap.hs:28-41,87-88 -- the layout is
+ * recalled from the packages, so every structural invariant is checked and anything else is refused) or the
+ * PPM catalogue it was generated from.  Replaces StarMap.readTreeFromFile (src/StarMap.hs:82-85). */
+int bsb_set_stars_file(bsb_ctx *ctx, const uint8_t *bytes, size_t len);
 size_t bsb_star_count(const bsb_ctx *ctx);
 
 /* ---- render: replaces Raytracer.render (src/Raytracer.hs:53-67) including the

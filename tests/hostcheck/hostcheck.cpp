@@ -124,6 +124,19 @@ long hc_parse_ppm(const uint8_t *bytes, size_t len, bsb_star *out, size_t cap, c
     return (long)v.size();
 }
 
+// a star map file as --starmap names it (stars.kdt or PPM): n stars, or -1 with the message in err
+long hc_parse_star_file(const uint8_t *bytes, size_t len, bsb_star *out, size_t cap, char *err, size_t errcap)
+{
+    std::vector<bsb_star> v;
+    std::string e;
+    if (!parse_star_file(bytes, len, v, e)) {
+        std::snprintf(err, errcap, "%s", e.c_str());
+        return -1;
+    }
+    for (size_t k = 0; k < v.size() && k < cap; k++) out[k] = v[k];
+    return (long)v.size();
+}
+
 // wall-clock milliseconds of build_star_tree (what bsb_set_stars spends on the host before the upload)
 double hc_build_tree_ms(const bsb_star *stars, size_t n, int reps)
 {

@@ -144,6 +144,21 @@ def test_bloom_vs_oracle(rnd, shape, divider):
     assert (got[..., 3] == 1).all()
 
 
+def test_stars_kdt_ingestion_equals_flat_list(rnd, scenes_dir):
+    # --starmap's own format: a tree file in the (recalled) stars.kdt layout renders the same frame as the flat list
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 160, 90)
+    ppm = starmap.synthetic_catalogue(30000, seed=9)
+    rnd.set_stars_file(starmap.catalogue_to_kdt(ppm))
+    assert rnd.star_count == 30000
+    a = rnd.render(cfg)
+    rnd.set_stars_file(ppm)
+    b = rnd.render(cfg)
+    np.testing.assert_array_equal(a, b)     # same star set -> same tree -> same bits
+    with pytest.raises(_lib.BlackstarError) as e:
+        rnd.set_stars_file(b"\x00\x00\x05 not a tree")
+    assert "neither" in e.value.message
+
+
 def test_bloom_full_frame_4096_vs_oracle(rnd, scenes_dir):
     """The WHOLE bloomed headline frame against the oracle (ImageFilters.hs:28-86): the rendered
     4096x4096 default-aa frame (stars + disk: point-like maxima next to black) goes through the

@@ -242,3 +242,39 @@ def test_star_tree_build_time(hc):
     ms = hc.hc_build_tree_ms(stars.ctypes.data, len(stars), 3)
     print(f"build_star_tree({len(stars)} stars): {ms:.1f} ms on this host")
     assert ms < 1500
+
+
+def test_stars_kdt_tree_file(hc):
+    """The reference's own star map file (stars.kdt, what --starmap defaults to, app/Main.hs:36): a tree file
+    written in the (recalled) cereal/kdt layout decodes to the same star set as the PPM catalogue it was made
+    from -- and anything that violates one of the layout's invariants is refused, not rendered."""
+    hc.hc_parse_star_file.restype = ctypes.c_long
+    hc.hc_parse_star_file.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    ppm = starmap.synthetic_catalogue(20000, seed=33)
+    want = starmap.read_ppm(ppm)
+    kdt = starmap.catalogue_to_kdt(ppm)
+    assert kdt[:3] == b"\x00\x00\x00" and len(kdt) == 2 + 20000 * (1 + 24 + 8 + 1 + 8) + 20001 + 8
+    out = np.zeros(20000, dtype=starmap.STAR_DTYPE)
+    err = ctypes.create_string_buffer(512)
+    assert hc.hc_parse_star_file(kdt, len(kdt), out.ctypes.data, len(out), err, 512) == 20000, err.value
+    key = lambda a: np.lexsort((a["pos"][:, 2], a["pos"][:, 1], a["pos"][:, 0]))
+    got, ref = out[key(out)], want[key(want)]
+    for f in ("pos", "mag", "hue", "sat"):
+        np.testing.assert_array_equal(got[f], ref[f])
+    # the same entry point still takes the catalogue itself
+    assert hc.hc_parse_star_file(ppm, len(ppm), out.ctypes.data, len(out), err, 512) == 20000
+    # refusals: truncated, a flipped tag, a perturbed coordinate (breaks axisValue == coordinate or the unit norm),
+    # a wrong size field, trailing bytes
+    bad = bytearray(kdt)
+    assert hc.hc_parse_star_file(bytes(bad[:-9]), len(bad) - 9, out.ctypes.data, len(out), err, 512) == -1
+    bad = bytearray(kdt); bad[2] = 7
+    assert hc.hc_parse_star_file(bytes(bad), len(bad), out.ctypes.data, len(out), err, 512) == -1
+    i = kdt.index(b"\x01\x3f") if b"\x01\x3f" in kdt else 40
+    bad = bytearray(kdt); bad[len(bad) // 2] ^= 0x10
+    assert hc.hc_parse_star_file(bytes(bad), len(bad), out.ctypes.data, len(out), err, 512) == -1
+    bad = bytearray(kdt); bad[-1] ^= 1
+    assert hc.hc_parse_star_file(bytes(bad), len(bad), out.ctypes.data, len(out), err, 512) == -1 and b"size" in err.value
+    bad = bytearray(kdt) + b"\x00"
+    assert hc.hc_parse_star_file(bytes(bad), len(bad), out.ctypes.data, len(out), err, 512) == -1
+    junk = np.random.default_rng(1).integers(0, 256, 5000, dtype=np.uint8).tobytes()
+    assert hc.hc_parse_star_file(junk, len(junk), out.ctypes.data, len(out), err, 512) == -1 and b"neither" in err.value
