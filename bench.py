@@ -270,6 +270,12 @@ def nccl_log_summary(pattern, world):
             continue
     for ln in lines[:world]:
         print(ln, file=sys.stderr)
+    if pattern.startswith(tempfile.gettempdir()) and "bsb_nccl_" in pattern:
+        for f in files:                       # our own scratch files: do not leave them behind
+            try:
+                os.remove(f)
+            except OSError:
+                pass
     return {"nranks_seen": sorted(nranks), "nranks_ok": world in nranks if nranks else None, "version": version,
             "log_files": len(files)}
 

@@ -218,6 +218,11 @@ int ensure(bsb_ctx *ctx, T *&ptr, size_t &cap, size_t need)
     if (need <= cap) return BSB_OK;
     if (ptr) BSB_CUDA(ctx, cudaFree(ptr));
     ptr = nullptr; cap = 0;
+    // 1/8 of slack: the row tiles of a multi-GPU ctx are re-cut from measured rates every frame, and a tile that
+    // grows by a few rows must not cost a cudaFree + cudaMalloc (both synchronise the device)
+    const size_t want = need + need / 8;
+    if (cudaMalloc(reinterpret_cast<void **>(&ptr), want * sizeof(T)) == cudaSuccess) { cap = want; return BSB_OK; }
+    (void)cudaGetLastError();
     BSB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ptr), need * sizeof(T)));
     cap = need;
     return BSB_OK;
