@@ -89,7 +89,7 @@ def test_frame_sharded_batch_equals_single_renders(tmp_path):
     a.nFrames = 6
     a.scene.resolution = (160, 90)
     stars = starmap.synthetic_stars(30000, seed=4)
-    n = max(1, min(2, torch.cuda.device_count()))
+    n = max(1, min(8, torch.cuda.device_count()))   # every GPU of the box: frame i -> GPU i mod n
     rs = [Renderer(devices=[k]) for k in range(n)]
     for r in rs:
         r.set_stars(stars)
