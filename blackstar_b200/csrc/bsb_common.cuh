@@ -78,8 +78,8 @@ struct FrameParams {
     double hsq6;              // h*h/6
     double h3;                // h/3
     double k13, k23;          // 1/3, 2/3: the step constants in the kernel's units (time in half steps)
-    double k14;               // 1.4 (the constant of the |pos|^-5 correction; an FP64 immediate carries
-                              // only a high word, so it lives in the constant bank / a register)
+    double k14;               // 1.4, the constant of the |pos|^-5 correction (the kernel now uses the literal:
+                              // ptxas keeps it in a register either way, and the literal build is 0.9 % faster)
     // termination / disk: src/Raytracer.hs:58-65, 88-111
     double safe2, din2, dout2;
     double r_in, r_out;       // sqrt of din2, dout2 (diskColor' recomputes them per hit)

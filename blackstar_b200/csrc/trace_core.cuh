@@ -90,27 +90,13 @@ BSB_HD void norm2_seed(double pu, double pv, double &q, double &y0)
 }
 
 // 0.4 q^(-5/2) from q and a seed y0 ~ q^-1/2 (see rinv5)
-#ifndef BSB_G_ORDER
-#define BSB_G_ORDER 0
-#endif
 BSB_HD double rinv5_seeded(double q, double y0, double k14)
 {
     const double s = y0 * y0;
     const double c = fma_(-q, s, k14);
-#if BSB_G_ORDER == 1
-    const double t = s * y0;
-    return (t * c) * s;
-#elif BSB_G_ORDER == 2
-    const double s2 = s * s;
-    return s2 * (y0 * c);
-#elif BSB_G_ORDER == 3
-    const double t = s * y0;
-    return (s * t) * c;
-#else
-    const double s2 = s * s;
-    const double y5 = s2 * y0;
+    const double s2 = s * s;        // this association, (s^2 y0) c, is the fastest of the four that were
+    const double y5 = s2 * y0;      // timed (profiles/r02_trace_variants.txt): up to 4 % between them
     return y5 * c;
-#endif
 }
 
 BSB_HD long long dbits(double x)
@@ -370,11 +356,7 @@ BSB_HD void disk_layer(const FrameParams &P, double r2ave, double acc[4])
 BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double &du, double &dv,
                      double &nu, double &nv, double &nq, double k14)
 {
-#if defined(BSB_K3_LITERAL)
-    const double k13 = 1.0 / 3.0, k23 = 2.0 / 3.0;
-#else
     const double k13 = P.k13, k23 = P.k23;
-#endif
     const double g1 = rinv5_seeded(q, rsqrt_seed(q), k14);
     const double a1u = g1 * u, a1v = g1 * v;
     const double p2u = u + du, p2v = v + dv;
@@ -385,16 +367,8 @@ BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double 
     double q3, y3;
     norm2_seed(p3u, p3v, q3, y3);
     const double g3 = rinv5_seeded(q3, y3, k14);
-#if defined(BSB_PE_ADD)
-    const double peu = p2u + du, pev = p2v + dv;
-#else
     const double peu = fma_(2.0, du, u), pev = fma_(2.0, dv, v);
-#endif
-#if defined(BSB_C2_MUL)
-    const double c2 = 2.0 * g2;
-#else
     const double c2 = g2 + g2;
-#endif
     const double p4u = fma_(-c2, p2u, peu), p4v = fma_(-c2, p2v, pev);
     double q4, y4;
     norm2_seed(p4u, p4v, q4, y4);
@@ -403,13 +377,8 @@ BSB_HD void rk4_step(const FrameParams &P, double u, double v, double q, double 
     const double du4 = fma_(g4, p4u, -a1u), dv4 = fma_(g4, p4v, -a1v);
     nu = fma_(-k23, su, peu);
     nv = fma_(-k23, sv, pev);
-#if defined(BSB_DU_SPLIT)
-    du = fma_(-k23, su, fma_(-k13, du4, du));
-    dv = fma_(-k23, sv, fma_(-k13, dv4, dv));
-#else
     du = fma_(-k13, fma_(2.0, su, du4), du);     // vel' = vel - 1/3 (2 S + D): 0.5 % faster than two FMAs with 2/3 and 1/3
     dv = fma_(-k13, fma_(2.0, sv, dv4), dv);
-#endif
     nq = fma_(nu, nu, nv * nv);
 }
 
@@ -425,11 +394,7 @@ BSB_HD void ray_advance(const FrameParams &P, RayState &s, uint32_t max_steps)
 {
     double ua = s.u, va = s.v, qa = s.q, du = s.du, dv = s.dv;
     double ub = ua, vb = va, qb = qa;
-#if defined(BSB_K14_PARAM)
-    const double k14 = P.k14;
-#else
     const double k14 = 1.4;      // as a literal: 0.9 % faster than from the constant bank (profiles/r02_trace_variants.txt)
-#endif
     // q > 0, so doubles order like their bit patterns.  Fast test on the high words: strictly
     // between the two thresholds' high words => neither the horizon nor the escape test fires.
     const long long qh = dbits(s.qh), qs = dbits(s.qs);
