@@ -957,9 +957,10 @@ int render_full_multi(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
     if (bloom) {
         const int rc = bloom_radius(ctx, W, H, scn->bloom_divider, &r);
         if (rc) return rc;
-        if (W > bloom_max_line() || H > bloom_max_line())
-            return fail(ctx, BSB_ERR_UNSUPPORTED, "multi-GPU bloom: image side above 8192 (use a 1-GPU ctx: it has the long-line path)");
     }
+    // sides above 8192 pixels: the bloom's long-line path runs on one GPU (the reference has no size limit, so
+    // neither may this): tiles are traced on all GPUs, copied to the first one over NVLink, bloomed there
+    const bool gather_bloom = bloom && (W > bloom_max_line() || H > bloom_max_line());
     std::vector<int> r0, r1, c0(n), c1(n);
     plan_row_tiles(ctx, H, r0, r1);
     for (int k = 0; k < n; k++) {   // column bands: equal, even boundaries
@@ -967,6 +968,42 @@ int render_full_multi(bsb_ctx *ctx, const bsb_camera *cam, const bsb_scene *scn,
         c1[k] = k == n - 1 ? W : std::max(c0[k], std::min(W, (int)((long long)W * (k + 1) / n) & ~1));
     }
     int launches = 0, rc;
+    if (gather_bloom) {
+        DeviceState &d0 = ctx->devs[0];
+        const size_t npix = (size_t)W * H;
+        BSB_CUDA(ctx, cudaSetDevice(d0.dev));
+        if ((rc = ensure(ctx, d0.d_aux, d0.aux_cap, npix))) return rc;
+        if (want_rgb8 && (rc = ensure(ctx, d0.d_u8, d0.u8_cap, npix * 3 + 16))) return rc;
+        for (int k = 0; k < n; k++) {
+            DeviceState &d = ctx->devs[k];
+            const int hk = r1[k] - r0[k];
+            BSB_CUDA(ctx, cudaSetDevice(d.dev));
+            if ((rc = ensure(ctx, d.d_frame, d.frame_cap, (size_t)hk * W + 1))) return rc;
+            if ((rc = trace_async(ctx, d, cam, scn, r0[k], r1[k], d.d_frame, d.ev[0], d.ev[1]))) return rc;
+            d.last_rows = hk;
+            launches += hk > 0 ? 2 : 0;
+            BSB_CUDA(ctx, cudaEventRecord(d.ev[5], d.stream));
+            BSB_CUDA(ctx, cudaEventRecord(d.ev[2], d.stream));
+            BSB_CUDA(ctx, cudaEventRecord(d.ev[3], d.stream));
+        }
+        BSB_CUDA(ctx, cudaSetDevice(d0.dev));
+        for (int k = 0; k < n; k++) {
+            DeviceState &d = ctx->devs[k];
+            const size_t cnt = (size_t)(r1[k] - r0[k]) * W;
+            if (cnt == 0) continue;
+            BSB_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d.ev[1], 0));
+            BSB_CUDA(ctx, cudaMemcpyPeerAsync(d0.d_aux + (size_t)r0[k] * W, d0.dev, d.d_frame, d.dev, cnt * sizeof(float4), d0.stream));
+        }
+        BSB_CUDA(ctx, cudaEventRecord(d0.ev[2], d0.stream));
+        if ((rc = bloom_async(ctx, d0, scn->bloom_strength, scn->bloom_divider, W, H, d0.d_aux, want_float ? d0.d_aux : nullptr,
+                              want_rgb8 ? d0.d_u8 : nullptr, &launches)))
+            return rc;
+        BSB_CUDA(ctx, cudaEventRecord(d0.ev[3], d0.stream));
+        if (want_float) res.f32.push_back(Band{ &d0, reinterpret_cast<const uint8_t *>(d0.d_aux), 0, (size_t)W * 16, 0, H });
+        if (want_rgb8) res.u8.push_back(Band{ &d0, d0.d_u8, 0, (size_t)W * 3, 0, H });
+        st->launches = launches; st->n_gpus = n; st->rays = rays_of(scn, H);
+        return BSB_OK;
+    }
     for (int k = 0; k < n; k++) {
         DeviceState &d = ctx->devs[k];
         const int hk = r1[k] - r0[k], wk = c1[k] - c0[k];

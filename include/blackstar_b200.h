@@ -35,7 +35,7 @@ extern "C" {
 #define BSB_ERR_INVALID 1   /* bad argument (NULL, negative size, rows out of range ...) */
 #define BSB_ERR_CUDA 2      /* a CUDA runtime call failed */
 #define BSB_ERR_NCCL 3      /* NCCL missing or a NCCL call failed (multi-GPU only) */
-#define BSB_ERR_UNSUPPORTED 4 /* e.g. multi-GPU bloom of an image side above 8192 */
+#define BSB_ERR_UNSUPPORTED 4 /* e.g. an image row above 8 MB in a staged host copy */
 #define BSB_ERR_STEPCAP 5   /* a ray hit the step cap (the reference would loop forever) */
 
 typedef struct bsb_ctx bsb_ctx;

@@ -58,6 +58,26 @@ def test_render_full_on_1_and_n_gpus(scenes_dir, scene, res):
         assert d8.max() <= 1 and (d8 != 0).mean() < 1e-4
 
 
+def test_sides_above_8192_on_n_gpus(scenes_dir):
+    """Bloom lines longer than the shared-memory kernel takes: on a multi-GPU ctx the tiles are traced everywhere,
+    copied to the first GPU over NVLink and bloomed there by the long-line path.  Against the 1-GPU render."""
+    cfg = config.with_resolution(config.load_config(f"{scenes_dir}/default.yaml"), 8208, 24)
+    stars = starmap.synthetic_stars(50000, seed=8)
+    with Renderer(devices=[0]) as r1:
+        r1.set_stars(stars)
+        ref = r1.do_render(cfg)
+        ref8 = r1.do_render_srgb8(cfg)
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("one GPU visible: needs gpurun --gpus 2")
+    with Renderer(n_gpus=min(n, 3)) as rk:
+        rk.set_stars(stars)
+        got = rk.do_render(cfg)
+        got8 = rk.do_render_srgb8(cfg)
+    np.testing.assert_array_equal(got, ref)        # same kernels on the same frame: bit-identical
+    np.testing.assert_array_equal(got8, ref8)
+
+
 @pytest.mark.parametrize("res,bloom", [((640, 362), True), ((1920, 1080), True), ((300, 168), False)])
 def test_one_process_per_gpu_pipeline(scenes_dir, tmp_path, res, bloom):
     """blackstar_b200.dist.DistributedFrame under torchrun on every visible GPU (>= 2): the frame that lands
