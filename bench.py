@@ -509,6 +509,42 @@ def run_b200(args):
         if rank == 0:
             nccl = nccl_log_summary(nccl_log, world)
 
+    # ---------------------------------------------------------------- the other arm, as a cross-check
+    # Under torchrun the numbers above come from one process per GPU.  The library's own multi-GPU path
+    # (ONE process, bsb_create(N), bsb_render_full_srgb8: csrc/bsb_api.cu render_full_multi) is what a
+    # reference-side shim would call, so rank 0 runs a few frames through it on the same N GPUs once the
+    # process group is gone, and reports them beside the headline (`inlib`); a failure there is reported,
+    # not fatal.
+    inlib = None
+    if multi_proc and rank == 0:
+        try:
+            with stdout_to_stderr():
+                rl = Renderer(n_gpus=world)
+            rl.set_stars(stars)
+            buf8 = np.zeros((H, W, 3), dtype=np.uint8)
+            for _ in range(3):
+                rl.do_render_srgb8(cfg, out=buf8)      # re-cuts the row tiles from the measured rates
+            k = max(3, min(args.steps, 10))
+            rl.synchronize()
+            t = time.perf_counter()
+            for _ in range(k):
+                rl.render_full_device(cfg, want_float=True, want_rgb8=False)
+            rl.synchronize()
+            dev_ms = (time.perf_counter() - t) * 1e3 / k
+            t = time.perf_counter()
+            for _ in range(k):
+                rl.do_render_srgb8(cfg, out=buf8)
+            e2e_l_ms = (time.perf_counter() - t) * 1e3 / k
+            st = dict(rl.last_stats)
+            rl.close()
+            inlib = {"value": rays_per_frame / (dev_ms * 1e-3) / 1e6, "ms_per_step": dev_ms,
+                     "e2e": {"value": rays_per_frame / (e2e_l_ms * 1e-3) / 1e6, "ms_per_step": e2e_l_ms,
+                             "path": "bsb_render_full_srgb8, one process driving all GPUs, plain-malloc buffer"},
+                     "frames": k, "stages_ms": {x: st[x] for x in ("trace_ms", "gather_ms", "bloom_ms", "d2h_ms")},
+                     "note": "wall clock on rank 0 after the process group was destroyed; the other ranks are exiting"}
+        except Exception as e:  # noqa: BLE001
+            inlib = {"error": str(e)[:300]}
+
     if rank == 0:
         counts = trace_kernel_counts()
         traffic = counts.get("dram_bytes_per_launch")
@@ -563,6 +599,8 @@ def run_b200(args):
         }
         if nccl is not None:
             line["nccl"] = nccl
+        if inlib is not None:
+            line["inlib"] = inlib
         if bloom_ms:
             bb = 2.0 * W * H * 16
             line["roofline_bloom"] = {"bound": "hbm", "kernel": "box3_kernel x2 (bloom)", "achieved": bb / (bloom_ms * 1e-3) / 1e9,
