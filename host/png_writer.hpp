@@ -2,7 +2,12 @@
 // Raytracer.writeImg, src/Raytracer.hs:29-32: 8-bit RGB, non-interlaced).
 #pragma once
 
+#include <sched.h>
 #include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include <algorithm>
 #include <cstdint>
@@ -72,11 +77,31 @@ inline std::string write_rgb8(const std::string &path, const uint8_t *rgb, int w
 // band is an independent raw-deflate stream ended with a sync flush, the last one with the final
 // block; one zlib header in front, the combined Adler-32 behind).  PNG encoding is the slow part
 // of writeImg for large frames; this makes it scale with host cores.
+// CPUs this process may actually use: the scheduler affinity and the cgroup v2 quota, not what the machine has
+// (hardware_concurrency() is 128+ on a GPU host whose container may use 16: one deflate thread per "core" then
+// means an order of magnitude of oversubscription and quota throttling).
+inline int usable_cpus()
+{
+    int n = (int)std::max(1u, std::thread::hardware_concurrency());
+#if defined(__linux__)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = std::min(n, std::max(1, CPU_COUNT(&set)));
+    if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[32] = "";
+        long long period = 0;
+        if (std::fscanf(f, "%31s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0)
+            n = std::min(n, std::max(1, (int)((std::atoll(q) + period / 2) / period)));
+        std::fclose(f);
+    }
+#endif
+    return n;
+}
+
 inline std::string write_rgb8_parallel(const std::string &path, const uint8_t *rgb, int width, int height,
                                        int threads = 0, int level = 6)
 {
     if (width <= 0 || height <= 0) return "bad image size";
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (threads <= 0) threads = usable_cpus();
     const int bands = std::max(1, std::min(threads, height / 16));
     if (bands == 1) return write_rgb8(path, rgb, width, height, level);
     const size_t stride = (size_t)width * 3;

@@ -118,6 +118,21 @@ def run_c5(n, n_frames, keep_png, png_level=6):
                     p = os.path.join(work, f"out{k}", name)
                     if os.path.exists(p):
                         shutil.copy(p, os.path.join(keep_png, "c5_" + name))
+        # ---- (a') ONE copy of the executable over all GPUs: every frame is row-tiled over the N GPUs of one ctx
+        # (bsb_create(0)), one background writer deflates with all host cores while the next frame is traced
+        for k in range(n):
+            for f in os.listdir(os.path.join(work, f"in{k}")):
+                shutil.copy(os.path.join(work, f"in{k}", f), os.path.join(work, "all", f))
+        env = dict(os.environ, BSB_PNG_LEVEL=str(png_level))
+        env.pop("CUDA_VISIBLE_DEVICES", None)
+        t0 = time.perf_counter()
+        pr = subprocess.run([exe, "-f", "-s", ppm, "-o", os.path.join(work, "out_all"), os.path.join(work, "all")], env=env,
+                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        dt = time.perf_counter() - t0
+        n_png = len([f for f in os.listdir(os.path.join(work, "out_all")) if f.endswith(".png")]) if os.path.isdir(os.path.join(work, "out_all")) else 0
+        rep["with_png_one_process"] = {"seconds": dt, "frames_per_s": n_png / dt, "pngs_written": n_png, "rc": pr.returncode,
+                                       "includes": "ONE process, one ctx over all GPUs (each frame row-tiled over them), one "
+                                                   "background PNG writer deflating with every host core", "stderr_tail": pr.stderr[-200:]}
         # ---- (b) the device side alone: same frames, same sharding, RGB8 into host memory, no encoder
         cfgs = animation.generate_frames(anim)
         rs = [Renderer(devices=[k]) for k in range(n)]
@@ -178,7 +193,7 @@ def main():
                 brief["C4 " + k] = {"value_Mrays_s": c4[k]["value"], "ms": c4[k]["ms_per_step"], "e2e_ms": c4[k]["e2e"]["ms_per_step"]}
         brief["C4 stats"] = c4.get("bsb_stats_srgb8")
     if "C5_animation" in rep:
-        brief["C5"] = {k: rep["C5_animation"].get(k) for k in ("with_png", "render_only", "bottleneck")}
+        brief["C5"] = {k: rep["C5_animation"].get(k) for k in ("with_png", "with_png_one_process", "render_only", "bottleneck")}
         brief["C5 zlib level 1"] = rep["C5_animation_png_level1"].get("with_png")
     print(json.dumps(brief, indent=1))
 
