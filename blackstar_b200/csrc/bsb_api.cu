@@ -346,8 +346,12 @@ int copy_bands_to_host(bsb_ctx *ctx, void *dst, size_t row_bytes, int rows, cons
     if (pe != cudaSuccess) (void)cudaGetLastError();
     const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     // small frames (a 1080p RGB8 image is 6 MB) are not worth waking the copy threads for: the driver's own
-    // staged copy takes well under a millisecond, and batch jobs run one such process per GPU
-    if (pinned || bytes < 2 * kStageChunk || ctx->copy_threads <= 0) {
+    // staged copy takes well under a millisecond, and batch jobs run one such process per GPU.  That holds for
+    // full-width bands only: a 2-D copy into PAGEABLE memory is staged by the driver row by row (measured:
+    // ~70 us per row, 150 ms for the two column bands of a 1080p frame), so those always go through the ring.
+    bool full_width = true;
+    for (const Band &b : bands) full_width = full_width && b.band_bytes == row_bytes;
+    if (pinned || ctx->copy_threads <= 0 || (full_width && bytes < 2 * kStageChunk)) {
         for (const Band &b : bands) {
             BSB_CUDA(ctx, cudaSetDevice(b.d->dev));
             uint8_t *row = out + (size_t)b.row0 * row_bytes;
