@@ -27,6 +27,21 @@ def test_row_tiles_partition():
             assert max(r1 - r0 for r0, r1 in t) - min(r1 - r0 for r0, r1 in t) <= 1
 
 
+def test_even_tiles_and_bands_partition_everything():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 9000), st.integers(1, 8))
+    def check(size, world):
+        for cut in (even_row_tiles(size, world), col_bands(size, world)):
+            assert len(cut) == world and cut[0][0] == 0 and cut[-1][1] == size
+            assert all(a[1] == b[0] for a, b in zip(cut, cut[1:])) and all(b >= a for a, b in cut)
+            assert all(a % 2 == 0 for a, _ in cut)           # interior boundaries are even (pairs of lines)
+            if size >= 4 * world:                            # big enough: nobody is empty, nobody has twice the share
+                assert min(b - a for a, b in cut) >= 1 and max(b - a for a, b in cut) <= size // world + 3
+    check()
+
+
 def test_balanced_tiles():
     # equal rates, no extra work -> the plain split
     assert balanced_tiles(4096, [10.0] * 8, [0.0] * 8) == row_tiles(4096, 8)
